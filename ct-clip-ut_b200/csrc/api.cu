@@ -1,0 +1,39 @@
+// C-ABI glue that is not tied to one kernel family.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+#include "ctc_internal.h"
+
+namespace ctc {
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace ctc
+
+using namespace ctc;
+
+extern "C" int ctc_version(void) { return CTC_VERSION; }
+extern "C" const char* ctc_last_error(void) { return g_err; }
+
+extern "C" int ctc_device_check(void) {
+    int dev = 0;
+    CTC_CHECK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CTC_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    CTC_REQUIRE(prop.major == 10, "ctclip_b200 is sm_100a only: device %d (%s) is sm_%d%d; there is no fallback path",
+                dev, prop.name, prop.major, prop.minor);
+    return 0;
+}
+
+extern "C" int ctc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldc, int M,
+                             int N, int K, int epi, const float* bias, const float* resid, int64_t ldr, int impl,
+                             void* stream) {
+    CTC_REQUIRE(epi == CTC_EPI_BF16 || epi == CTC_EPI_F32, "ctc_gemm_bf16: epilogue %d not available through this entry", epi);
+    return gemm_bf16(A, lda, B, ldb, out, ldc, M, N, K, epi, bias, resid, ldr, nullptr, nullptr, impl,
+                     (cudaStream_t)stream);
+}

@@ -1,0 +1,625 @@
+// Fused cosine-similarity attention for the factorised CTViT transformer
+// (reference: Attention.forward, src/utils/attention.py:144-180):
+//     q^ = l2norm(q) * q_scale,  k^ = l2norm(k) * k_scale
+//     P  = softmax(scale * q^ k^T + bias),   O = P v
+// One kernel family serves both sequence modes (ctvit.py:94-101) without ever materialising the
+// '(b t) (h w) d' <-> '(b h w) t d' rearranges: SPATIAL sequences are the H*W tokens of a (b,t)
+// slice, TEMPORAL sequences are the T tokens of a (b,h,w) column, addressed by stride.
+//
+// Shapes on this path: d_head = 32, n = 576 (spatial) or 24 (temporal), 8 heads.  The whole K/V of
+// one (sequence, head) fits shared memory (36 KB each at n = 576), so there is no K/V streaming:
+// a CTA loads + normalises K/V once, each warp owns 16 query rows and walks the keys in blocks
+// of 64 with an online softmax.  The l2norm, q/k scales, softmax scale and the relative-position
+// bias (a (2H-1)(2W-1) table per head held in shared memory instead of the reference's
+// [heads, n, n] tensor) are all fused.  Matrix products use warp-level mma.sync m16n8k16 bf16
+// with fp32 accumulation (the d=32 core is exp/LDS-bound, not MMA-bound: SURVEY §7 hard part 3).
+//
+// Backward (input gradients only) recomputes P from the saved row log-sum-exp:
+//   kernel dQ  : per 64-query block  — dP = dO V^T, dS = P∘(dP − D), dQ^ = dS K^, l2norm/scale adjoint
+//   kernel dKV : per 64-key block    — the transposed problem for dV = P^T dO, dK^ = dS^T Q^
+#include "common.cuh"
+#include "ctc_internal.h"
+
+namespace ctc {
+
+static constexpr int DH = 32;          // head dim (fixed on this path: inference_ctclip.py:29)
+static constexpr int QB = 64;          // query rows (or key rows in dKV) per CTA
+static constexpr int KB = 64;          // keys per online-softmax step
+static constexpr float LOG2E = 1.4426950408889634f;
+static constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnParams {
+    const __nv_bfloat16* q; long long ldq;
+    const __nv_bfloat16* k; const __nv_bfloat16* v; long long ldkv;
+    const __nv_bfloat16* o; const __nv_bfloat16* d_o;   // [R, heads*32]
+    const float* q_scale; const float* k_scale; float scale;
+    const float* bias_table;  // [heads, (2H-1)*(2W-1)] or null
+    int n, n_pad, n_seq, heads, mode, T, HW, H, W;
+    __nv_bfloat16* out; float* lse;                      // fwd outputs
+    float* probs;                                        // probs kernel output
+    __nv_bfloat16* dq; long long lddq; __nv_bfloat16* dk; __nv_bfloat16* dv; long long lddkv;
+    float* delta;                                        // [R, heads]
+};
+
+CTC_DEVINL long long seq_row(const AttnParams& p, int s, int i) {
+    if (p.mode == CTC_MODE_SPATIAL) return (long long)s * p.HW + i;
+    const int b = s / p.HW, hw = s % p.HW;
+    return ((long long)b * p.T + i) * p.HW + hw;
+}
+// 64-byte rows (32 bf16), 16-byte chunks XOR-swizzled so that ldmatrix is bank-conflict free
+CTC_DEVINL uint32_t tile_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+// Load `rows` rows of 32 bf16 (row i of the sequence at src + seq_row*ld + head*32) into a swizzled tile.
+// NORM: l2-normalise and multiply by vec[d] * mul (fp32 math).  Rows >= n are zero-filled.
+template <bool NORM>
+CTC_DEVINL void load_tile(uint8_t* tile, const __nv_bfloat16* src, long long ld, const AttnParams& p, int s, int head,
+                          int row0, int rows, const float* vec, float mul) {
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        const int i = row0 + r;
+        uint4 c[4];
+        if (i < p.n) {
+            const uint4* g = reinterpret_cast<const uint4*>(src + seq_row(p, s, i) * ld + head * DH);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = g[j];
+            if (NORM) {
+                float f[32];
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 t = unpack_bf16(w[e]);
+                        f[j * 8 + e * 2] = t.x; f[j * 8 + e * 2 + 1] = t.y;
+                        ss += t.x * t.x + t.y * t.y;
+                    }
+                }
+                const float inv = mul / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    c[j].x = pack_bf16(f[j * 8 + 0] * inv * vec[j * 8 + 0], f[j * 8 + 1] * inv * vec[j * 8 + 1]);
+                    c[j].y = pack_bf16(f[j * 8 + 2] * inv * vec[j * 8 + 2], f[j * 8 + 3] * inv * vec[j * 8 + 3]);
+                    c[j].z = pack_bf16(f[j * 8 + 4] * inv * vec[j * 8 + 4], f[j * 8 + 5] * inv * vec[j * 8 + 5]);
+                    c[j].w = pack_bf16(f[j * 8 + 6] * inv * vec[j * 8 + 6], f[j * 8 + 7] * inv * vec[j * 8 + 7]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(tile + tile_off(r, j)) = c[j];
+    }
+}
+
+// A fragments (16 rows x 32 dims = 2 k-steps) of the warp's row block from a swizzled tile
+CTC_DEVINL void load_a_frags(uint32_t (&a)[2][4], uint32_t tile_addr, int row0, int lane) {
+    const int r = row0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) ldmatrix_x4(a[ks], tile_addr + tile_off(r, ks * 2 + (lane >> 4)));
+}
+// acc(16 x 8) += A(16 x 32) * B^T where B rows (8 of them, starting at row n0) are "n rows x 32 k"
+CTC_DEVINL void mma_rowsB(float (&acc)[4], const uint32_t (&a)[2][4], uint32_t tile_addr, int n0, int lane) {
+    uint32_t b[4];
+    ldmatrix_x4(b, tile_addr + tile_off(n0 + (lane & 7), lane >> 3));
+    mma_bf16_16816(acc, a[0], b[0], b[1]);
+    mma_bf16_16816(acc, a[1], b[2], b[3]);
+}
+// acc[4](16 x 32) += A(16 x 16) * B where B rows k0..k0+15 are "k rows x 32 n" (transposed load)
+CTC_DEVINL void mma_colsB(float (&acc)[4][4], const uint32_t (&a)[4], uint32_t tile_addr, int k0, int lane) {
+    const int r = k0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, tile_addr + tile_off(r, dp * 2 + (lane >> 4)));
+        mma_bf16_16816(acc[dp * 2], a, b[0], b[1]);
+        mma_bf16_16816(acc[dp * 2 + 1], a, b[2], b[3]);
+    }
+}
+
+
+// common prologue: q/k scale vectors, bias table (pre-multiplied by log2e), key index table
+CTC_DEVINL void load_bias(const AttnParams& p, int head, float* bias, int* tab, int count) {
+    if (p.bias_table) {
+        const int nb = (2 * p.H - 1) * (2 * p.W - 1);
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) bias[i] = p.bias_table[(long long)head * nb + i] * LOG2E;
+        const int nW = 2 * p.W - 1;
+        for (int j = threadIdx.x; j < count; j += blockDim.x) {
+            const int jj = min(j, p.n - 1);   // padded keys are masked later; keep the index in range
+            tab[j] = (jj / p.W) * nW + (jj % p.W);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward (PROBS=false) / probability materialisation (PROBS=true)
+// ---------------------------------------------------------------------------------------------
+template <bool PROBS>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const AttnParams p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    const int qb = blockIdx.z, head = blockIdx.y, s = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* ks = sm;
+    uint8_t* vs = ks + p.n_pad * 64;
+    uint8_t* qs = vs + p.n_pad * 64;
+    float* sv = reinterpret_cast<float*>(qs + QB * 64);   // 64 floats: q_scale, k_scale
+    int* tabj = reinterpret_cast<int*>(sv + 64);
+    float* bias = reinterpret_cast<float*>(tabj + p.n_pad);
+    if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
+    else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
+    load_bias(p, head, bias, tabj, p.n_pad);
+    __syncthreads();
+    load_tile<true>(ks, p.k, p.ldkv, p, s, head, 0, p.n_pad, sv + 32, 1.0f);
+    if (!PROBS) load_tile<false>(vs, p.v, p.ldkv, p, s, head, 0, p.n_pad, nullptr, 1.0f);
+    load_tile<true>(qs, p.q, p.ldq, p, s, head, qb * QB, QB, sv, p.scale * LOG2E);
+    __syncthreads();
+
+    const int row_base = qb * QB + warp * 16;
+    if (row_base >= p.n) return;
+    const uint32_t ks_a = smem_u32(ks), vs_a = smem_u32(vs), qs_a = smem_u32(qs);
+    uint32_t aq[2][4];
+    load_a_frags(aq, qs_a, warp * 16, lane);
+    const int g = lane >> 2, t = lane & 3;
+    const int i0 = row_base + g, i1 = i0 + 8;
+    const int nW = 2 * p.W - 1;
+    const bool has_bias = p.bias_table != nullptr;
+    int base0 = 0, base1 = 0;
+    if (has_bias) {
+        base0 = (min(i0, p.n - 1) / p.W + p.H - 1) * nW + (min(i0, p.n - 1) % p.W + p.W - 1);
+        base1 = (min(i1, p.n - 1) / p.W + p.H - 1) * nW + (min(i1, p.n - 1) % p.W + p.W - 1);
+    }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float oacc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) oacc[a][b] = 0.f;
+    float lse2_0 = 0.f, lse2_1 = 0.f;
+    if (PROBS) {
+        lse2_0 = (i0 < p.n) ? p.lse[seq_row(p, s, i0) * p.heads + head] * LOG2E : 0.f;
+        lse2_1 = (i1 < p.n) ? p.lse[seq_row(p, s, i1) * p.heads + head] * LOG2E : 0.f;
+    }
+
+    for (int kb = 0; kb < p.n_pad / KB; ++kb) {
+        float sc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+            mma_rowsB(sc[nt], aq, ks_a, kb * KB + nt * 8, lane);
+            const int j = kb * KB + nt * 8 + 2 * t;
+            if (has_bias) {
+                const int tj0 = tabj[j], tj1 = tabj[j + 1];
+                sc[nt][0] += bias[base0 - tj0]; sc[nt][1] += bias[base0 - tj1];
+                sc[nt][2] += bias[base1 - tj0]; sc[nt][3] += bias[base1 - tj1];
+            }
+            if (j >= p.n) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
+            if (j + 1 >= p.n) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
+        }
+        if (PROBS) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int j = kb * KB + nt * 8 + 2 * t;
+                if (i0 < p.n) {
+                    float* pr = p.probs + (((long long)s * p.heads + head) * p.n + i0) * p.n + j;
+                    if (j < p.n) pr[0] = exp2f(sc[nt][0] - lse2_0);
+                    if (j + 1 < p.n) pr[1] = exp2f(sc[nt][1] - lse2_0);
+                }
+                if (i1 < p.n) {
+                    float* pr = p.probs + (((long long)s * p.heads + head) * p.n + i1) * p.n + j;
+                    if (j < p.n) pr[0] = exp2f(sc[nt][2] - lse2_1);
+                    if (j + 1 < p.n) pr[1] = exp2f(sc[nt][3] - lse2_1);
+                }
+            }
+            continue;
+        }
+        // online softmax (log2 domain)
+        float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+            bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+        const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+        const float c0 = exp2f(m0 - nm0), c1 = exp2f(m1 - nm1);
+        m0 = nm0; m1 = nm1;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            sc[nt][0] = exp2f(sc[nt][0] - m0); sc[nt][1] = exp2f(sc[nt][1] - m0);
+            sc[nt][2] = exp2f(sc[nt][2] - m1); sc[nt][3] = exp2f(sc[nt][3] - m1);
+            rs0 += sc[nt][0] + sc[nt][1]; rs1 += sc[nt][2] + sc[nt][3];
+        }
+        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { oacc[a][0] *= c0; oacc[a][1] *= c0; oacc[a][2] *= c1; oacc[a][3] *= c1; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t a[4];
+            a[0] = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]);
+            a[1] = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
+            a[2] = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+            a[3] = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+            mma_colsB(oacc, a, vs_a, kb * KB + kk * 16, lane);
+        }
+    }
+    if (PROBS) return;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    if (i0 < p.n) {
+        const long long r = seq_row(p, s, i0);
+        __nv_bfloat16* orow = p.out + r * (p.heads * DH) + head * DH;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<uint32_t*>(orow + a * 8 + 2 * t) = pack_bf16(oacc[a][0] * inv0, oacc[a][1] * inv0);
+        if (t == 0) p.lse[r * p.heads + head] = (m0 + log2f(l0)) * LN2;
+    }
+    if (i1 < p.n) {
+        const long long r = seq_row(p, s, i1);
+        __nv_bfloat16* orow = p.out + r * (p.heads * DH) + head * DH;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<uint32_t*>(orow + a * 8 + 2 * t) = pack_bf16(oacc[a][2] * inv1, oacc[a][3] * inv1);
+        if (t == 0) p.lse[r * p.heads + head] = (m1 + log2f(l1)) * LN2;
+    }
+}
+
+// adjoint of x^ = l2norm(x) * vec for one row held in mma C layout (quad of lanes owns the row):
+// gacc = gradient w.r.t. (x^ / mul'), i.e. caller passes g already multiplied by everything but vec.
+// Returns dx for the 8 elements this thread owns (cols a*8 + 2t, +1 for a = 0..3).
+CTC_DEVINL void l2norm_adjoint_row(const __nv_bfloat16* xrow, const float* vec, int t, float (&g)[8], float (&dx)[8]) {
+    float x[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(xrow + a * 8 + 2 * t));
+        x[a * 2] = v.x; x[a * 2 + 1] = v.y;
+        ss += v.x * v.x + v.y * v.y;
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    float dot = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        g[a * 2] *= vec[a * 8 + 2 * t]; g[a * 2 + 1] *= vec[a * 8 + 2 * t + 1];
+        x[a * 2] *= inv; x[a * 2 + 1] *= inv;
+        dot += x[a * 2] * g[a * 2] + x[a * 2 + 1] * g[a * 2 + 1];
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1); dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dx[e] = (g[e] - x[e] * dot) * inv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, dQ: one CTA per (64-query block, head, sequence)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const AttnParams p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    const int qb = blockIdx.z, head = blockIdx.y, s = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* ks = sm;
+    uint8_t* vs = ks + p.n_pad * 64;
+    uint8_t* qs = vs + p.n_pad * 64;
+    uint8_t* dos = qs + QB * 64;
+    float* sv = reinterpret_cast<float*>(dos + QB * 64);
+    float* dl = sv + 64;                                   // D for the 64 rows
+    int* tabj = reinterpret_cast<int*>(dl + QB);
+    float* bias = reinterpret_cast<float*>(tabj + p.n_pad);
+    if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
+    else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
+    load_bias(p, head, bias, tabj, p.n_pad);
+    __syncthreads();
+    load_tile<true>(ks, p.k, p.ldkv, p, s, head, 0, p.n_pad, sv + 32, 1.0f);
+    load_tile<false>(vs, p.v, p.ldkv, p, s, head, 0, p.n_pad, nullptr, 1.0f);
+    load_tile<true>(qs, p.q, p.ldq, p, s, head, qb * QB, QB, sv, p.scale * LOG2E);
+    load_tile<false>(dos, p.d_o, (long long)p.heads * DH, p, s, head, qb * QB, QB, nullptr, 1.0f);
+    // D_i = sum_d dO_i,d * O_i,d   (thread per row)
+    if (threadIdx.x < QB) {
+        const int i = qb * QB + threadIdx.x;
+        float d = 0.f;
+        if (i < p.n) {
+            const long long r = seq_row(p, s, i);
+            const uint4* go = reinterpret_cast<const uint4*>(p.o + r * (p.heads * DH) + head * DH);
+            const uint4* gd = reinterpret_cast<const uint4*>(p.d_o + r * (p.heads * DH) + head * DH);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 a = go[j], b = gd[j];
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 x = unpack_bf16(aw[e]), y = unpack_bf16(bw[e]);
+                    d += x.x * y.x + x.y * y.y;
+                }
+            }
+            p.delta[r * p.heads + head] = d;
+        }
+        dl[threadIdx.x] = d;
+    }
+    __syncthreads();
+
+    const int row_base = qb * QB + warp * 16;
+    if (row_base >= p.n) return;
+    const uint32_t ks_a = smem_u32(ks), vs_a = smem_u32(vs), qs_a = smem_u32(qs), dos_a = smem_u32(dos);
+    uint32_t aq[2][4], ado[2][4];
+    load_a_frags(aq, qs_a, warp * 16, lane);
+    load_a_frags(ado, dos_a, warp * 16, lane);
+    const int g = lane >> 2, t = lane & 3;
+    const int i0 = row_base + g, i1 = i0 + 8;
+    const int nW = 2 * p.W - 1;
+    const bool has_bias = p.bias_table != nullptr;
+    int base0 = 0, base1 = 0;
+    if (has_bias) {
+        base0 = (min(i0, p.n - 1) / p.W + p.H - 1) * nW + (min(i0, p.n - 1) % p.W + p.W - 1);
+        base1 = (min(i1, p.n - 1) / p.W + p.H - 1) * nW + (min(i1, p.n - 1) % p.W + p.W - 1);
+    }
+    const float lse2_0 = (i0 < p.n) ? p.lse[seq_row(p, s, i0) * p.heads + head] * LOG2E : INFINITY;
+    const float lse2_1 = (i1 < p.n) ? p.lse[seq_row(p, s, i1) * p.heads + head] * LOG2E : INFINITY;
+    const float d0 = dl[warp * 16 + g], d1 = dl[warp * 16 + g + 8];
+    float dq[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dq[a][b] = 0.f;
+
+    for (int kb = 0; kb < p.n_pad / KB; ++kb) {
+        float sc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+            mma_rowsB(sc[nt], aq, ks_a, kb * KB + nt * 8, lane);
+            const int j = kb * KB + nt * 8 + 2 * t;
+            if (has_bias) {
+                const int tj0 = tabj[j], tj1 = tabj[j + 1];
+                sc[nt][0] += bias[base0 - tj0]; sc[nt][1] += bias[base0 - tj1];
+                sc[nt][2] += bias[base1 - tj0]; sc[nt][3] += bias[base1 - tj1];
+            }
+            float dp[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_rowsB(dp, ado, vs_a, kb * KB + nt * 8, lane);
+            const float p0 = (j < p.n) ? exp2f(sc[nt][0] - lse2_0) : 0.f;
+            const float p1 = (j + 1 < p.n) ? exp2f(sc[nt][1] - lse2_0) : 0.f;
+            const float p2 = (j < p.n) ? exp2f(sc[nt][2] - lse2_1) : 0.f;
+            const float p3 = (j + 1 < p.n) ? exp2f(sc[nt][3] - lse2_1) : 0.f;
+            sc[nt][0] = p0 * (dp[0] - d0); sc[nt][1] = p1 * (dp[1] - d0);
+            sc[nt][2] = p2 * (dp[2] - d1); sc[nt][3] = p3 * (dp[3] - d1);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t a[4];
+            a[0] = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]);
+            a[1] = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
+            a[2] = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+            a[3] = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+            mma_colsB(dq, a, ks_a, kb * KB + kk * 16, lane);
+        }
+    }
+    // dq^ -> dq through l2norm and q_scale; ds/dq^_d = scale * q_scale_d * k^_d  (k^ includes k_scale)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int i = half ? i1 : i0;
+        if (i >= p.n) continue;
+        const long long r = seq_row(p, s, i);
+        float gq[8], dx[8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { gq[a * 2] = dq[a][half * 2] * p.scale; gq[a * 2 + 1] = dq[a][half * 2 + 1] * p.scale; }
+        l2norm_adjoint_row(p.q + r * p.ldq + head * DH, sv, t, gq, dx);
+        __nv_bfloat16* drow = p.dq + r * p.lddq + head * DH;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<uint32_t*>(drow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, dK/dV: one CTA per (64-key block, head, sequence); queries are the reduction axis
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const AttnParams p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    const int kblk = blockIdx.z, head = blockIdx.y, s = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* qs = sm;                                       // all queries (scaled q^)
+    uint8_t* dos = qs + p.n_pad * 64;                       // all dO rows
+    uint8_t* ks = dos + p.n_pad * 64;                       // my 64 keys (k^)
+    uint8_t* vs = ks + QB * 64;                             // my 64 values
+    float* sv = reinterpret_cast<float*>(vs + QB * 64);
+    float* lse2 = sv + 64;                                  // [n_pad]
+    float* dl = lse2 + p.n_pad;                             // [n_pad]
+    int* basei = reinterpret_cast<int*>(dl + p.n_pad);      // [n_pad]
+    float* bias = reinterpret_cast<float*>(basei + p.n_pad);
+    if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
+    else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
+    const int nW = 2 * p.W - 1;
+    const bool has_bias = p.bias_table != nullptr;
+    if (has_bias) {
+        const int nb = (2 * p.H - 1) * nW;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) bias[i] = p.bias_table[(long long)head * nb + i] * LOG2E;
+        for (int i = threadIdx.x; i < p.n_pad; i += blockDim.x) {
+            const int ii = min(i, p.n - 1);
+            basei[i] = (ii / p.W + p.H - 1) * nW + (ii % p.W + p.W - 1);
+        }
+    }
+    for (int i = threadIdx.x; i < p.n_pad; i += blockDim.x) {
+        if (i < p.n) {
+            const long long r = seq_row(p, s, i);
+            lse2[i] = p.lse[r * p.heads + head] * LOG2E;
+            dl[i] = p.delta[r * p.heads + head];
+        } else { lse2[i] = INFINITY; dl[i] = 0.f; }
+    }
+    __syncthreads();
+    load_tile<true>(qs, p.q, p.ldq, p, s, head, 0, p.n_pad, sv, p.scale * LOG2E);
+    load_tile<false>(dos, p.d_o, (long long)p.heads * DH, p, s, head, 0, p.n_pad, nullptr, 1.0f);
+    load_tile<true>(ks, p.k, p.ldkv, p, s, head, kblk * QB, QB, sv + 32, 1.0f);
+    load_tile<false>(vs, p.v, p.ldkv, p, s, head, kblk * QB, QB, nullptr, 1.0f);
+    __syncthreads();
+
+    const int row_base = kblk * QB + warp * 16;
+    if (row_base >= p.n) return;
+    const uint32_t ks_a = smem_u32(ks), vs_a = smem_u32(vs), qs_a = smem_u32(qs), dos_a = smem_u32(dos);
+    uint32_t ak[2][4], av[2][4];
+    load_a_frags(ak, ks_a, warp * 16, lane);
+    load_a_frags(av, vs_a, warp * 16, lane);
+    const int g = lane >> 2, t = lane & 3;
+    const int j0 = row_base + g, j1 = j0 + 8;
+    int tab0 = 0, tab1 = 0;
+    if (has_bias) {
+        tab0 = (min(j0, p.n - 1) / p.W) * nW + min(j0, p.n - 1) % p.W;
+        tab1 = (min(j1, p.n - 1) / p.W) * nW + min(j1, p.n - 1) % p.W;
+    }
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { dk[a][b] = 0.f; dv[a][b] = 0.f; }
+
+    for (int qb = 0; qb < p.n_pad / KB; ++qb) {
+        float pt[8][4], ds[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            // S^T tile: rows = my keys, cols = queries
+            float st[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_rowsB(st, ak, qs_a, qb * KB + nt * 8, lane);
+            const int i = qb * KB + nt * 8 + 2 * t;
+            if (has_bias) {
+                const int b0 = basei[i], b1 = basei[i + 1];
+                st[0] += bias[b0 - tab0]; st[1] += bias[b1 - tab0];
+                st[2] += bias[b0 - tab1]; st[3] += bias[b1 - tab1];
+            }
+            const float l0 = lse2[i], l1 = lse2[i + 1];
+            pt[nt][0] = exp2f(st[0] - l0); pt[nt][1] = exp2f(st[1] - l1);
+            pt[nt][2] = exp2f(st[2] - l0); pt[nt][3] = exp2f(st[3] - l1);
+            float dp[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_rowsB(dp, av, dos_a, qb * KB + nt * 8, lane);
+            const float dd0 = dl[i], dd1 = dl[i + 1];
+            ds[nt][0] = pt[nt][0] * (dp[0] - dd0); ds[nt][1] = pt[nt][1] * (dp[1] - dd1);
+            ds[nt][2] = pt[nt][2] * (dp[2] - dd0); ds[nt][3] = pt[nt][3] * (dp[3] - dd1);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t a[4];
+            a[0] = pack_bf16(pt[2 * kk][0], pt[2 * kk][1]);
+            a[1] = pack_bf16(pt[2 * kk][2], pt[2 * kk][3]);
+            a[2] = pack_bf16(pt[2 * kk + 1][0], pt[2 * kk + 1][1]);
+            a[3] = pack_bf16(pt[2 * kk + 1][2], pt[2 * kk + 1][3]);
+            mma_colsB(dv, a, dos_a, qb * KB + kk * 16, lane);
+            a[0] = pack_bf16(ds[2 * kk][0], ds[2 * kk][1]);
+            a[1] = pack_bf16(ds[2 * kk][2], ds[2 * kk][3]);
+            a[2] = pack_bf16(ds[2 * kk + 1][0], ds[2 * kk + 1][1]);
+            a[3] = pack_bf16(ds[2 * kk + 1][2], ds[2 * kk + 1][3]);
+            mma_colsB(dk, a, qs_a, qb * KB + kk * 16, lane);
+        }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int j = half ? j1 : j0;
+        if (j >= p.n) continue;
+        const long long r = seq_row(p, s, j);
+        __nv_bfloat16* dvrow = p.dv + r * p.lddkv + head * DH;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<uint32_t*>(dvrow + a * 8 + 2 * t) = pack_bf16(dv[a][half * 2], dv[a][half * 2 + 1]);
+        // dk^ accumulated against q^ * scale * log2e  ->  undo log2e; k_scale applied inside the adjoint
+        float gk[8], dx[8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { gk[a * 2] = dk[a][half * 2] * LN2; gk[a * 2 + 1] = dk[a][half * 2 + 1] * LN2; }
+        l2norm_adjoint_row(p.k + r * p.ldkv + head * DH, sv + 32, t, gk, dx);
+        __nv_bfloat16* dkrow = p.dk + r * p.lddkv + head * DH;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<uint32_t*>(dkrow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+    }
+}
+
+static int fill_params(AttnParams& p, int B, int T, int H, int W, int heads, int mode) {
+    CTC_REQUIRE(mode == CTC_MODE_SPATIAL || mode == CTC_MODE_TEMPORAL, "attention: bad mode %d", mode);
+    p.heads = heads; p.mode = mode; p.T = T; p.HW = H * W; p.H = H; p.W = W;
+    p.n = (mode == CTC_MODE_SPATIAL) ? H * W : T;
+    p.n_seq = (mode == CTC_MODE_SPATIAL) ? B * T : B * H * W;
+    p.n_pad = (p.n + KB - 1) / KB * KB;
+    CTC_REQUIRE(p.n_pad <= 1024, "attention: sequence length %d exceeds the shared-memory resident design (1024)", p.n);
+    return 0;
+}
+
+template <typename Kern>
+static int set_smem(Kern kern, size_t bytes, size_t& configured) {
+    if (bytes > configured) {
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    return 0;
+}
+
+}  // namespace ctc
+
+using namespace ctc;
+
+extern "C" int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int B, int T,
+                                 int H, int W, int heads, const float* q_scale, const float* k_scale, float scale,
+                                 const float* bias_table, int mode, void* o, float* lse, void* stream) {
+    AttnParams p{};
+    if (int e = fill_params(p, B, T, H, W, heads, mode)) return e;
+    p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
+    p.ldkv = ldkv; p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale; p.bias_table = bias_table;
+    p.out = (__nv_bfloat16*)o; p.lse = lse;
+    const size_t nb = bias_table ? (size_t)(2 * H - 1) * (2 * W - 1) : 0;
+    const size_t smem = (size_t)p.n_pad * 128 + QB * 64 + 256 + p.n_pad * 4 + nb * 4;
+    static size_t configured = 0;
+    if (int e = set_smem(attn_fwd_kernel<false>, smem, configured)) return e;
+    dim3 grid(p.n_seq, heads, (p.n + QB - 1) / QB);
+    attn_fwd_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(p);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_attention_probs(const void* q, int64_t ldq, const void* k, int64_t ldkv, const float* lse, int B,
+                                   int T, int H, int W, int heads, const float* q_scale, const float* k_scale,
+                                   float scale, const float* bias_table, int mode, float* probs, void* stream) {
+    AttnParams p{};
+    if (int e = fill_params(p, B, T, H, W, heads, mode)) return e;
+    p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.k = (const __nv_bfloat16*)k; p.v = nullptr; p.ldkv = ldkv;
+    p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale; p.bias_table = bias_table;
+    p.lse = const_cast<float*>(lse); p.probs = probs;
+    const size_t nb = bias_table ? (size_t)(2 * H - 1) * (2 * W - 1) : 0;
+    const size_t smem = (size_t)p.n_pad * 128 + QB * 64 + 256 + p.n_pad * 4 + nb * 4;
+    static size_t configured = 0;
+    if (int e = set_smem(attn_fwd_kernel<true>, smem, configured)) return e;
+    dim3 grid(p.n_seq, heads, (p.n + QB - 1) / QB);
+    attn_fwd_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(p);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_attention_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* o,
+                                 const void* d_o, const float* lse, int B, int T, int H, int W, int heads,
+                                 const float* q_scale, const float* k_scale, float scale, const float* bias_table,
+                                 int mode, void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* delta_ws,
+                                 void* stream) {
+    AttnParams p{};
+    if (int e = fill_params(p, B, T, H, W, heads, mode)) return e;
+    p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
+    p.ldkv = ldkv; p.o = (const __nv_bfloat16*)o; p.d_o = (const __nv_bfloat16*)d_o;
+    p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale; p.bias_table = bias_table;
+    p.lse = const_cast<float*>(lse); p.delta = delta_ws;
+    p.dq = (__nv_bfloat16*)dq; p.lddq = lddq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddkv = lddkv;
+    const size_t nb = bias_table ? (size_t)(2 * H - 1) * (2 * W - 1) : 0;
+    {
+        const size_t smem = (size_t)p.n_pad * 128 + 2 * QB * 64 + 256 + QB * 4 + p.n_pad * 4 + nb * 4;
+        static size_t configured = 0;
+        if (int e = set_smem(attn_bwd_dq_kernel, smem, configured)) return e;
+        dim3 grid(p.n_seq, heads, (p.n + QB - 1) / QB);
+        attn_bwd_dq_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
+        CTC_LAUNCH_CHECK();
+    }
+    {
+        const size_t smem = (size_t)p.n_pad * 128 + 2 * QB * 64 + 256 + 3 * p.n_pad * 4 + nb * 4;
+        static size_t configured = 0;
+        if (int e = set_smem(attn_bwd_dkv_kernel, smem, configured)) return e;
+        dim3 grid(p.n_seq, heads, (p.n + QB - 1) / QB);
+        attn_bwd_dkv_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
+        CTC_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -1,0 +1,264 @@
+// Attribution-side reductions (reference: src/utils/visualizations.py):
+//   attention rollout (:707-743 as driven by :800-841), raw-attention query means (:666,671),
+//   Grad-CAM channel weights + CAM (:933-991), integrated-gradients combine (:878-879),
+//   trilinear up-sampling with the fused rot90 (:289-293, :816).
+// All HBM-bound: coalesced 128-bit accesses, warp-shuffle reductions.
+#include "common.cuh"
+#include "ctc_internal.h"
+
+namespace ctc {
+
+// ---------------------------------------------------------------------------------------------
+// spatial "rollout": the reference calls attention_rollout([P_slice]) with ONE matrix, so
+//   A = mean_h P;  A /= (rowsum + 1e-8);  A += I;  A /= rowsum;  result = A @ I;  out = colsum(A)
+// One CTA per (slice, 8-row group): each warp owns a row, accumulates its column contributions
+// into shared memory, then one atomicAdd per column per CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rollout_spatial_kernel(const float* __restrict__ probs, int heads, int n, float* __restrict__ out) {
+    extern __shared__ float col[];  // [n]
+    const int s = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) col[j] = 0.f;
+    __syncthreads();
+    const float invh = 1.f / heads;
+    for (int i = blockIdx.y * nw + warp; i < n; i += gridDim.y * nw) {
+        // pass 1: row sum of the head mean
+        float rs = 0.f;
+        for (int j = lane; j < n; j += 32) {
+            float a = 0.f;
+            for (int h = 0; h < heads; ++h) a += probs[(((long long)s * heads + h) * n + i) * n + j];
+            rs += a * invh;
+        }
+        rs = warp_sum(rs);
+        const float d1 = rs + 1e-8f;
+        // second normaliser: sum_j (A_ij / d1) + 1
+        const float r2 = rs / d1 + 1.f;
+        for (int j = lane; j < n; j += 32) {
+            float a = 0.f;
+            for (int h = 0; h < heads; ++h) a += probs[(((long long)s * heads + h) * n + i) * n + j];
+            float v = a * invh / d1;
+            if (j == i) v += 1.f;
+            atomicAdd(&col[j], v / r2);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) atomicAdd(&out[(long long)s * n + j], col[j]);
+}
+
+// temporal rollout: chain L layers of [T, T] head-mean matrices per token (T <= 32): one warp per token,
+// lane = matrix row.  result = A_L ... A_1 (result = A @ result per layer); out = colsum(result).
+__global__ void __launch_bounds__(128)
+rollout_temporal_kernel(const float* __restrict__ probs, int n_layers, int n_tok, int heads, int T,
+                        float* __restrict__ out) {
+    __shared__ float res[4][32][33];
+    __shared__ float nxt[4][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tok = blockIdx.x * 4 + warp;
+    if (tok >= n_tok) return;
+    float (*R)[33] = res[warp];
+    float (*N)[33] = nxt[warp];
+    for (int j = 0; j < T; ++j) if (lane < T) R[lane][j] = (lane == j) ? 1.f : 0.f;
+    __syncwarp();
+    const long long layer_stride = (long long)n_tok * heads * T * T;
+    for (int l = 0; l < n_layers; ++l) {
+        float a[32];
+        float rs = 0.f;
+        if (lane < T) {
+            for (int j = 0; j < T; ++j) {
+                float v = 0.f;
+                for (int h = 0; h < heads; ++h)
+                    v += probs[l * layer_stride + (((long long)tok * heads + h) * T + lane) * T + j];
+                a[j] = v / heads;
+                rs += a[j];
+            }
+            const float d1 = rs + 1e-8f;
+            float r2 = 0.f;
+            for (int j = 0; j < T; ++j) { a[j] = a[j] / d1 + (j == lane ? 1.f : 0.f); r2 += a[j]; }
+            for (int j = 0; j < T; ++j) a[j] /= r2;
+            for (int c = 0; c < T; ++c) {
+                float v = 0.f;
+                for (int j = 0; j < T; ++j) v += a[j] * R[j][c];
+                N[lane][c] = v;
+            }
+        }
+        __syncwarp();
+        if (lane < T) for (int c = 0; c < T; ++c) R[lane][c] = N[lane][c];
+        __syncwarp();
+    }
+    if (lane < T) {
+        float v = 0.f;
+        for (int i = 0; i < T; ++i) v += R[i][lane];
+        out[(long long)tok * T + lane] = v;
+    }
+}
+
+// out[s, h, j] = mean_i P[s, h, i, j]; one CTA per (s, h), thread per column (coalesced rows)
+__global__ void __launch_bounds__(256)
+attn_colmean_kernel(const float* __restrict__ probs, int n, float* __restrict__ out) {
+    const long long sh = blockIdx.x;
+    const float* P = probs + sh * n * n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float a = 0.f;
+        for (int i = 0; i < n; ++i) a += P[(long long)i * n + j];
+        out[sh * n + j] = a / n;
+    }
+}
+
+// w[c] += sum_r g[r, c] / R over this CTA's row slab (w must be zeroed by the caller)
+__global__ void __launch_bounds__(256)
+colmean_kernel(const float* __restrict__ g, long long R, int C, float invR, float* __restrict__ w) {
+    const long long rows_per = (R + gridDim.x - 1) / gridDim.x;
+    const long long r0 = blockIdx.x * rows_per, r1 = min(R, r0 + rows_per);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f;
+        for (long long r = r0; r < r1; ++r) a += g[r * C + c];
+        atomicAdd(&w[c], a * invR);
+    }
+}
+
+// cam[r] = relu(sum_c (fa[r,c] - fb[r,c]) * w[c]); warp per row
+__global__ void __launch_bounds__(256)
+gradcam_kernel(const float* __restrict__ fa, const float* __restrict__ fb, const float* __restrict__ w, long long R,
+               int C, float* __restrict__ cam) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    float a = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 x = *reinterpret_cast<const float4*>(fa + row * C + c);
+        if (fb) {
+            const float4 y = *reinterpret_cast<const float4*>(fb + row * C + c);
+            x.x -= y.x; x.y -= y.y; x.z -= y.z; x.w -= y.w;
+        }
+        const float4 ww = *reinterpret_cast<const float4*>(w + c);
+        a += x.x * ww.x + x.y * ww.y + x.z * ww.z + x.w * ww.w;
+    }
+    a = warp_sum(a);
+    if (lane == 0) cam[row] = fmaxf(a, 0.f);
+}
+
+// F.interpolate(mode='trilinear', align_corners=False): src = max(0, (dst + 0.5) * in/out - 0.5)
+CTC_DEVINL void lerp_coord(int dst, int in, int out, int& i0, int& i1, float& w1) {
+    float s = ((float)dst + 0.5f) * ((float)in / (float)out) - 0.5f;
+    s = fmaxf(s, 0.f);
+    i0 = min((int)s, in - 1);
+    i1 = min(i0 + 1, in - 1);
+    w1 = s - (float)i0;
+}
+// thread per 4 consecutive output voxels along the fastest output axis
+__global__ void __launch_bounds__(256)
+upsample_kernel(const float* __restrict__ in, int d, int h, int w, float* __restrict__ out, int D, int H, int W, int rot) {
+    // un-rotated result up[z, y, x]; np.rot90(up, k=-1, axes=(1,2)) -> out[z, x, H-1-y] with shape [D, W, H]
+    const int OY = rot ? W : H, OX = rot ? H : W;
+    const long long total = (long long)D * OY * (OX / 4);
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox4 = (int)(idx % (OX / 4)) * 4;
+    const int oy = (int)((idx / (OX / 4)) % OY);
+    const int z = (int)(idx / ((long long)(OX / 4) * OY));
+    int z0, z1; float wz;
+    lerp_coord(z, d, D, z0, z1, wz);
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int ox = ox4 + e;
+        const int y = rot ? (H - 1 - ox) : oy;
+        const int x = rot ? oy : ox;
+        int y0, y1, x0, x1; float wy, wx;
+        lerp_coord(y, h, H, y0, y1, wy);
+        lerp_coord(x, w, W, x0, x1, wx);
+        auto at = [&](int zz, int yy, int xx) { return in[((long long)zz * h + yy) * w + xx]; };
+        const float c00 = at(z0, y0, x0) * (1.f - wx) + at(z0, y0, x1) * wx;
+        const float c01 = at(z0, y1, x0) * (1.f - wx) + at(z0, y1, x1) * wx;
+        const float c10 = at(z1, y0, x0) * (1.f - wx) + at(z1, y0, x1) * wx;
+        const float c11 = at(z1, y1, x0) * (1.f - wx) + at(z1, y1, x1) * wx;
+        const float c0 = c00 * (1.f - wy) + c01 * wy;
+        const float c1 = c10 * (1.f - wy) + c11 * wy;
+        r[e] = c0 * (1.f - wz) + c1 * wz;
+    }
+    *reinterpret_cast<float4*>(out + ((long long)z * OY + oy) * OX + ox4) = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+CTC_DEVINL void atomic_min_float(float* addr, float v) {   // v >= 0 only (relu output)
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+CTC_DEVINL void atomic_max_float(float* addr, float v) {
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+__global__ void __launch_bounds__(256)
+ig_combine_kernel(const float* __restrict__ vol, const float* __restrict__ gsum, long long n, float inv_steps,
+                  float* __restrict__ ig, float* __restrict__ mm) {
+    float mn = 3.0e38f, mx = 0.f;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+        const float4 x = *reinterpret_cast<const float4*>(vol + i);
+        const float4 g = *reinterpret_cast<const float4*>(gsum + i);
+        float4 o;
+        o.x = fmaxf((x.x - 1.f) * (g.x * inv_steps), 0.f); o.y = fmaxf((x.y - 1.f) * (g.y * inv_steps), 0.f);
+        o.z = fmaxf((x.z - 1.f) * (g.z * inv_steps), 0.f); o.w = fmaxf((x.w - 1.f) * (g.w * inv_steps), 0.f);
+        *reinterpret_cast<float4*>(ig + i) = o;
+        mn = fminf(mn, fminf(fminf(o.x, o.y), fminf(o.z, o.w)));
+        mx = fmaxf(mx, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+    }
+    mx = warp_max(mx);
+    mn = -warp_max(-mn);
+    if ((threadIdx.x & 31) == 0) { atomic_min_float(mm, mn); atomic_max_float(mm + 1, mx); }
+}
+
+}  // namespace ctc
+
+using namespace ctc;
+
+extern "C" int ctc_rollout_spatial(const float* probs, int n_slices, int heads, int n, float* out, void* stream) {
+    CTC_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)n_slices * n * sizeof(float), (cudaStream_t)stream));
+    dim3 grid(n_slices, 8);
+    rollout_spatial_kernel<<<grid, 256, n * sizeof(float), (cudaStream_t)stream>>>(probs, heads, n, out);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_rollout_temporal(const float* probs, int n_layers, int n_tok, int heads, int T, float* out,
+                                    void* stream) {
+    CTC_REQUIRE(T <= 32, "rollout_temporal: T=%d exceeds 32", T);
+    rollout_temporal_kernel<<<(n_tok + 3) / 4, 128, 0, (cudaStream_t)stream>>>(probs, n_layers, n_tok, heads, T, out);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_attn_colmean(const float* probs, int n_seq, int heads, int n, float* out, void* stream) {
+    attn_colmean_kernel<<<n_seq * heads, 256, 0, (cudaStream_t)stream>>>(probs, n, out);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_colmean(const float* g, int R, int C, float* w, void* stream) {
+    CTC_CHECK_CUDA(cudaMemsetAsync(w, 0, (size_t)C * sizeof(float), (cudaStream_t)stream));
+    const int grid = R < 592 ? R : 592;
+    colmean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, R, C, 1.f / (float)R, w);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_gradcam(const float* fa, const float* fb, const float* w, int R, int C, float* cam, void* stream) {
+    CTC_REQUIRE(C % 4 == 0, "gradcam: C=%d must be a multiple of 4", C);
+    gradcam_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(fa, fb, w, R, C, cam);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_upsample_trilinear(const float* in, int d, int h, int w, float* out, int D, int H, int W, int rot90,
+                                      void* stream) {
+    CTC_REQUIRE(H % 4 == 0 && W % 4 == 0, "upsample: H=%d, W=%d must be multiples of 4", H, W);
+    const long long total = (long long)D * H * W / 4;
+    upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, d, h, w, out, D, H, W, rot90);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_ig_combine(const float* volume, const float* gsum, int64_t n, float inv_steps, float* ig, float* mm,
+                              void* stream) {
+    CTC_REQUIRE(n % 4 == 0, "ig_combine: n must be a multiple of 4");
+    ig_combine_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(volume, gsum, n, inv_steps, ig, mm);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,295 @@
+// HBM-bound row / stencil kernels of the CTViT path: LayerNorm fwd/bwd, PEG depthwise 3x3x3
+// stencil (+adjoint), GEGLU fwd/bwd, continuous-position-bias table.
+// All are bandwidth kernels: 128-bit vector accesses, one warp per 512-wide row, warp-shuffle
+// reductions, grids sized well above 148 SMs x resident CTAs.
+#include "common.cuh"
+#include "ctc_internal.h"
+
+namespace ctc {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row. Row (<= 4 KB) is re-read from L1 for the three passes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, int R, int C, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y_bf16,
+                     float* __restrict__ y_f32, __nv_bfloat16* __restrict__ xraw) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const float* xr = x + (long long)row * C;
+    float s = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+        float4 o;
+        o.x = (v.x - mean) * rstd * g.x; o.y = (v.y - mean) * rstd * g.y;
+        o.z = (v.z - mean) * rstd * g.z; o.w = (v.w - mean) * rstd * g.w;
+        if (beta) {
+            const float4 b = *reinterpret_cast<const float4*>(beta + c);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        const long long off = (long long)row * C + c;
+        if (y_f32) *reinterpret_cast<float4*>(y_f32 + off) = o;
+        if (y_bf16) *reinterpret_cast<uint2*>(y_bf16 + off) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        if (xraw) *reinterpret_cast<uint2*>(xraw + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+
+// LayerNorm backward (input gradient only — attribution never needs weight gradients).
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int R, int C,
+                     const float* __restrict__ gamma, float eps, float* __restrict__ out, int accumulate,
+                     __nv_bfloat16* __restrict__ out_bf16) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const float* xr = x + (long long)row * C;
+    const float* gr = dy + (long long)row * C;
+    float s = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    float sg = 0.f, sgx = 0.f;  // sum(g), sum(g * xhat), g = dy * gamma
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        const float4 d = *reinterpret_cast<const float4*>(gr + c);
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+        const float g0 = d.x * gm.x, g1 = d.y * gm.y, g2 = d.z * gm.z, g3 = d.w * gm.w;
+        sg += (g0 + g1) + (g2 + g3);
+        sgx += g0 * (v.x - mean) * rstd + g1 * (v.y - mean) * rstd + g2 * (v.z - mean) * rstd + g3 * (v.w - mean) * rstd;
+    }
+    sg = warp_sum(sg) / C;
+    sgx = warp_sum(sgx) / C;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        const float4 d = *reinterpret_cast<const float4*>(gr + c);
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+        float4 o;
+        o.x = rstd * (d.x * gm.x - sg - (v.x - mean) * rstd * sgx);
+        o.y = rstd * (d.y * gm.y - sg - (v.y - mean) * rstd * sgx);
+        o.z = rstd * (d.z * gm.z - sg - (v.z - mean) * rstd * sgx);
+        o.w = rstd * (d.w * gm.w - sg - (v.w - mean) * rstd * sgx);
+        const long long off = (long long)row * C + c;
+        if (accumulate) {
+            const float4 p = *reinterpret_cast<const float4*>(out + off);
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        *reinterpret_cast<float4*>(out + off) = o;
+        if (out_bf16)
+            *reinterpret_cast<uint2*>(out_bf16 + off) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PEG: depthwise 3x3x3 stencil over the token grid, channels-last, 4 channels per thread.
+// Kernel tap (a, b, c) (the Conv3d kernel indices over the reinterpreted (t',h',w') axes, with
+// causal padding (2,0) on t' and (1,1) on h', w') maps to a canonical-grid offset:
+//   SPATIAL : (dt, dh, dw) = (a-2, b-1, c-1)
+//   TEMPORAL: (t',h',w') = (h, w, t)  =>  (dt, dh, dw) = (c-1, a-2, b-1)
+// The adjoint (transpose=1) gathers with the negated offsets.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+peg_kernel(const float* __restrict__ x, int B, int T, int H, int W, int C, const float* __restrict__ w27,
+           const float* __restrict__ bias, int mode, int sign, float* __restrict__ y,
+           __nv_bfloat16* __restrict__ y_bf16) {
+    const int c4 = C >> 2;
+    const long long total = (long long)B * T * H * W * c4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % c4) * 4;
+    long long tok = idx / c4;
+    const int w = (int)(tok % W);
+    const int h = (int)((tok / W) % H);
+    const int t = (int)((tok / ((long long)W * H)) % T);
+    const long long base_b = (tok / ((long long)W * H * T)) * T * H * W;
+    const float4 self = *reinterpret_cast<const float4*>(x + tok * C + c);
+    float4 acc = self;
+    if (bias && sign > 0) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + c);
+        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                int dt, dh, dw;
+                if (mode == CTC_MODE_SPATIAL) { dt = a - 2; dh = b - 1; dw = cc - 1; }
+                else { dt = cc - 1; dh = a - 2; dw = b - 1; }
+                const int tt = t + sign * dt, hh = h + sign * dh, ww = w + sign * dw;
+                if (tt < 0 || tt >= T || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+                const float4 v = *reinterpret_cast<const float4*>(x + (base_b + ((long long)tt * H + hh) * W + ww) * C + c);
+                const float4 k = *reinterpret_cast<const float4*>(w27 + ((a * 3 + b) * 3 + cc) * C + c);
+                acc.x += v.x * k.x; acc.y += v.y * k.y; acc.z += v.z * k.z; acc.w += v.w * k.w;
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(y + tok * C + c) = acc;
+    if (y_bf16)
+        *reinterpret_cast<uint2*>(y_bf16 + tok * C + c) = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEGLU
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+geglu_fwd_kernel(const __nv_bfloat16* __restrict__ u, long long R, int F, __nv_bfloat16* __restrict__ h) {
+    const int f8 = F >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * f8) return;
+    const long long r = idx / f8;
+    const int f = (int)(idx % f8) * 8;
+    const uint4 xa = *reinterpret_cast<const uint4*>(u + r * 2 * F + f);
+    const uint4 ga = *reinterpret_cast<const uint4*>(u + r * 2 * F + F + f);
+    const uint32_t xs[4] = {xa.x, xa.y, xa.z, xa.w}, gs[4] = {ga.x, ga.y, ga.z, ga.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 xv = unpack_bf16(xs[i]), gv = unpack_bf16(gs[i]);
+        o[i] = pack_bf16(gelu_erf(gv.x) * xv.x, gelu_erf(gv.y) * xv.y);
+    }
+    *reinterpret_cast<uint4*>(h + r * F + f) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256)
+geglu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ dh, long long R, int F,
+                 __nv_bfloat16* __restrict__ du) {
+    const int f8 = F >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * f8) return;
+    const long long r = idx / f8;
+    const int f = (int)(idx % f8) * 8;
+    const uint4 xa = *reinterpret_cast<const uint4*>(u + r * 2 * F + f);
+    const uint4 ga = *reinterpret_cast<const uint4*>(u + r * 2 * F + F + f);
+    const uint4 da = *reinterpret_cast<const uint4*>(dh + r * F + f);
+    const uint32_t xs[4] = {xa.x, xa.y, xa.z, xa.w}, gs[4] = {ga.x, ga.y, ga.z, ga.w}, ds[4] = {da.x, da.y, da.z, da.w};
+    uint32_t ox[4], og[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 xv = unpack_bf16(xs[i]), gv = unpack_bf16(gs[i]), dv = unpack_bf16(ds[i]);
+        ox[i] = pack_bf16(gelu_erf(gv.x) * dv.x, gelu_erf(gv.y) * dv.y);
+        og[i] = pack_bf16(xv.x * gelu_erf_grad(gv.x) * dv.x, xv.y * gelu_erf_grad(gv.y) * dv.y);
+    }
+    *reinterpret_cast<uint4*>(du + r * 2 * F + f) = make_uint4(ox[0], ox[1], ox[2], ox[3]);
+    *reinterpret_cast<uint4*>(du + r * 2 * F + F + f) = make_uint4(og[0], og[1], og[2], og[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Continuous position bias table: one CTA per relative offset, MLP 2 -> dim -> dim -> heads.
+// ---------------------------------------------------------------------------------------------
+__global__ void cpb_table_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
+                                 const float* __restrict__ w1, const float* __restrict__ b1,
+                                 const float* __restrict__ w2, const float* __restrict__ b2, int dim, int heads,
+                                 int H, int W, float* __restrict__ table) {
+    extern __shared__ float sm[];
+    float* h1 = sm;
+    float* h2 = sm + dim;
+    const int nW = 2 * W - 1;
+    const int off = blockIdx.x;
+    const int dh = off / nW - (H - 1), dw = off % nW - (W - 1);
+    auto logd = [](int d) { return d == 0 ? 0.f : (d > 0 ? 1.f : -1.f) * logf(fabsf((float)d) + 1.f); };
+    const float p0 = logd(dh), p1 = logd(dw);
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+        const float v = w0[j * 2] * p0 + w0[j * 2 + 1] * p1 + b0[j];
+        h1[j] = v > 0.f ? v : 0.1f * v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+        float v = b1[j];
+        for (int k = 0; k < dim; ++k) v += w1[(long long)j * dim + k] * h1[k];
+        h2[j] = v > 0.f ? v : 0.1f * v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int hd = warp; hd < heads; hd += blockDim.x >> 5) {
+        float v = 0.f;
+        for (int k = lane; k < dim; k += 32) v += w2[(long long)hd * dim + k] * h2[k];
+        v = warp_sum(v);
+        if (lane == 0) table[(long long)hd * (2 * H - 1) * nW + off] = v + b2[hd];
+    }
+}
+
+}  // namespace ctc
+
+using namespace ctc;
+
+extern "C" int ctc_layernorm_fwd(const float* x, int R, int C, const float* gamma, const float* beta, float eps,
+                                 void* y_bf16, float* y_f32, void* xraw_bf16, void* stream) {
+    CTC_REQUIRE(C % 4 == 0 && R > 0, "layernorm_fwd: C=%d must be a multiple of 4, R=%d > 0", C, R);
+    layernorm_fwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        x, R, C, gamma, beta, eps, (__nv_bfloat16*)y_bf16, y_f32, (__nv_bfloat16*)xraw_bf16);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, const float* gamma, float eps,
+                                 float* out, int accumulate, void* out_bf16, void* stream) {
+    CTC_REQUIRE(C % 4 == 0 && R > 0, "layernorm_bwd: C=%d must be a multiple of 4, R=%d > 0", C, R);
+    layernorm_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dy, x, R, C, gamma, eps, out, accumulate,
+                                                                        (__nv_bfloat16*)out_bf16);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_peg(const float* x, int B, int T, int H, int W, int C, const float* w27, const float* bias,
+                       int mode, int transpose, float* y, void* y_bf16, void* stream) {
+    CTC_REQUIRE(C % 4 == 0, "peg: C=%d must be a multiple of 4", C);
+    CTC_REQUIRE(x != y, "peg: in-place stencil is not supported");
+    CTC_REQUIRE(mode == CTC_MODE_SPATIAL || (T == H && H == W),
+                "peg: temporal mode reinterprets (h,w,t) as (t,h,w) and needs T==H==W (got %d,%d,%d)", T, H, W);
+    const long long total = (long long)B * T * H * W * (C / 4);
+    peg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, B, T, H, W, C, w27, bias, mode, transpose ? -1 : 1, y, (__nv_bfloat16*)y_bf16);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_geglu_fwd(const void* u, int R, int F, void* h, void* stream) {
+    CTC_REQUIRE(F % 8 == 0, "geglu: F=%d must be a multiple of 8", F);
+    const long long total = (long long)R * (F / 8);
+    geglu_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)u, R, F, (__nv_bfloat16*)h);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_geglu_bwd(const void* u, const void* dh, int R, int F, void* du, void* stream) {
+    CTC_REQUIRE(F % 8 == 0, "geglu: F=%d must be a multiple of 8", F);
+    const long long total = (long long)R * (F / 8);
+    geglu_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)u, (const __nv_bfloat16*)dh, R, F, (__nv_bfloat16*)du);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_cpb_table(const float* w0, const float* b0, const float* w1, const float* b1, const float* w2,
+                             const float* b2, int dim, int heads, int H, int W, float* table, void* stream) {
+    const int n_off = (2 * H - 1) * (2 * W - 1);
+    cpb_table_kernel<<<n_off, 256, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(w0, b0, w1, b1, w2, b2, dim,
+                                                                                    heads, H, W, table);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}

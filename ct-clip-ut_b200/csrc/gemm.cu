@@ -1,0 +1,382 @@
+// Dense bf16 GEMM family for the CTViT linears:  C[M,N] = A[M,K] · B[N,K]ᵀ  (fp32 accumulate).
+//
+// sm_100a design: persistent, warp-specialised kernel, one CTA per SM.
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma kind::f16, M=128, N=BN, K=16)
+//   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4-7   epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// The accumulator lives in TMEM and is double buffered, so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  Both operands are K-major ("row-major [rows, K]"), which is exactly the
+// nn.Linear weight layout [out_features, in_features] (reference: src/utils/attention.py:47,49,
+// 119-120,124; src/utils/ctvit.py:50; src/models/ctclip.py:62-63).
+//
+// A plain SIMT kernel with the same epilogues (gemm_simt) is kept as a bring-up / cross-check
+// comparator for tests; the product path always uses the tcgen05 kernel.
+#include "common.cuh"
+#include "ctc_internal.h"
+
+namespace ctc {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int kStages = 4;
+static constexpr int kGemmThreads = 256;
+
+struct GemmArgs {
+    int M, N, K;
+    void* out;          // bf16 or fp32, row stride ldc (elements)
+    long long ldc;
+    const float* bias;  // [N] or null
+    const float* resid; // fp32 [M, ldr] or null (may alias out)
+    long long ldr;
+    float* top2_val;    // EPI_ARGMAX: [M, n_tiles*2]
+    int* top2_idx;
+    int n_tiles_n;
+};
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+// ---------------------------------------------------------------------------------------------
+// epilogue: one thread owns one accumulator row (TMEM lane) and 32 consecutive columns
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+CTC_DEVINL void epilogue_store(const GemmArgs& g, int row, int col0, const uint32_t (&acc)[32]) {
+    if (row >= g.M) return;
+    if constexpr (EPI == CTC_EPI_BF16) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(g.out) + (long long)row * g.ldc + col0;
+        if (col0 + 32 <= g.N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                uint4 q;
+                q.x = pack_bf16(__uint_as_float(acc[v * 8 + 0]), __uint_as_float(acc[v * 8 + 1]));
+                q.y = pack_bf16(__uint_as_float(acc[v * 8 + 2]), __uint_as_float(acc[v * 8 + 3]));
+                q.z = pack_bf16(__uint_as_float(acc[v * 8 + 4]), __uint_as_float(acc[v * 8 + 5]));
+                q.w = pack_bf16(__uint_as_float(acc[v * 8 + 6]), __uint_as_float(acc[v * 8 + 7]));
+                reinterpret_cast<uint4*>(out)[v] = q;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < g.N) out[j] = __float2bfloat16(__uint_as_float(acc[j]));
+        }
+    } else {  // fp32 output, optional bias and residual
+        float* out = reinterpret_cast<float*>(g.out) + (long long)row * g.ldc + col0;
+        const float* res = g.resid ? g.resid + (long long)row * g.ldr + col0 : nullptr;
+        const bool vec = (col0 + 32 <= g.N) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                         (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0);
+        if (vec) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                float4 o;
+                o.x = __uint_as_float(acc[v * 4 + 0]);
+                o.y = __uint_as_float(acc[v * 4 + 1]);
+                o.z = __uint_as_float(acc[v * 4 + 2]);
+                o.w = __uint_as_float(acc[v * 4 + 3]);
+                if (g.bias) {
+                    const float4 b = *reinterpret_cast<const float4*>(g.bias + col0 + v * 4);
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                if (res) {
+                    const float4 r = reinterpret_cast<const float4*>(res)[v];
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                reinterpret_cast<float4*>(out)[v] = o;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (col0 + j < g.N) {
+                    float o = __uint_as_float(acc[j]);
+                    if (g.bias) o += g.bias[col0 + j];
+                    if (res) o += res[j];
+                    out[j] = o;
+                }
+            }
+        }
+    }
+}
+
+// running top-2 (value, column) over a row, used by the VQ nearest-code search
+struct Top2 {
+    float v0, v1;
+    int i0, i1;
+    CTC_DEVINL void init() { v0 = v1 = -3.0e38f; i0 = i1 = 0; }
+    CTC_DEVINL void push(float v, int i) {
+        if (v > v0) { v1 = v0; i1 = i0; v0 = v; i0 = i; }
+        else if (v > v1) { v1 = v; i1 = i; }
+    }
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmArgs g) {
+    using S = GemmSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_m = (g.M + BM - 1) / BM;
+    const int tiles_n = (g.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int k_blocks = (g.K + BK - 1) / BK;
+    constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512 (power of two >= 32)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int tm = tile / tiles_n, tn = tile % tiles_n;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * S::kStageBytes;
+                    uint8_t* sb = sa + S::kABytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
+                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+                    const uint32_t sb = sa + S::kABytes;
+                    const uint64_t da = make_umma_desc_sw128(sa);
+                    const uint64_t db = make_umma_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr>>4) field
+                        umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                    (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp - 4;  // TMEM lane quarter: warp (id % 4) may only touch lanes 32*(id%4)..+31
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile / tiles_n, tn = tile % tiles_n;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = tm * BM + ew * 32 + lane;
+            const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
+            Top2 t2; t2.init();
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c, v);
+                tmem_ld_wait();
+                const int col0 = tn * BN + c;
+                if constexpr (EPI == CTC_EPI_ARGMAX) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < g.N) t2.push(__uint_as_float(v[j]), col0 + j);
+                } else {
+                    if (col0 < g.N) epilogue_store<EPI>(g, row, col0, v);
+                }
+            }
+            if constexpr (EPI == CTC_EPI_ARGMAX) {
+                if (row < g.M) {
+                    const long long o = ((long long)row * g.n_tiles_n + tn) * 2;
+                    g.top2_val[o] = t2.v0; g.top2_val[o + 1] = t2.v1;
+                    g.top2_idx[o] = t2.i0; g.top2_idx[o + 1] = t2.i1;
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT comparator (tests / bring-up only)
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, long long lda,
+                                 const __nv_bfloat16* __restrict__ B, long long ldb, const GemmArgs g) {
+    __shared__ float sa[16][17], sb[16][17];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < g.K; k0 += 16) {
+        const int ka = k0 + tx;
+        sa[ty][tx] = (row < g.M && ka < g.K) ? __bfloat162float(A[(long long)row * lda + ka]) : 0.f;
+        const int brow = blockIdx.x * 16 + ty;
+        sb[ty][tx] = (brow < g.N && ka < g.K) ? __bfloat162float(B[(long long)brow * ldb + ka]) : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[tx][k];
+        __syncthreads();
+    }
+    if (row >= g.M || col >= g.N) return;
+    if constexpr (EPI == CTC_EPI_BF16) {
+        reinterpret_cast<__nv_bfloat16*>(g.out)[(long long)row * g.ldc + col] = __float2bfloat16(acc);
+    } else {
+        if (g.bias) acc += g.bias[col];
+        if (g.resid) acc += g.resid[(long long)row * g.ldr + col];
+        reinterpret_cast<float*>(g.out)[(long long)row * g.ldc + col] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with row stride ld (elements); box = [box_rows, 64]
+static int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
+                          int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    CTC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    CTC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand not 16-byte aligned");
+    CTC_REQUIRE((ld * 2) % 16 == 0, "GEMM operand row stride (%lld elements) is not a multiple of 16 bytes", ld);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CTC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int BN, int EPI>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
+    using S = GemmSmem<BN>;
+    static bool configured = false;
+    if (!configured) {
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            S::kTotal));
+        configured = true;
+    }
+    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, g);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldc, int M, int N,
+              int K, int epi, const float* bias, const float* resid, long long ldr, float* top2_val, int* top2_idx,
+              int impl, cudaStream_t st) {
+    CTC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K; g.out = out; g.ldc = ldc; g.bias = bias; g.resid = resid; g.ldr = ldr;
+    g.top2_val = top2_val; g.top2_idx = top2_idx;
+    if (impl == CTC_GEMM_SIMT) {
+        CTC_REQUIRE(epi != CTC_EPI_ARGMAX, "gemm: SIMT comparator has no arg-max epilogue");
+        dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
+        if (epi == CTC_EPI_BF16)
+            gemm_simt_kernel<CTC_EPI_BF16><<<grid, block, 0, st>>>((const __nv_bfloat16*)A, lda,
+                                                                   (const __nv_bfloat16*)B, ldb, g);
+        else
+            gemm_simt_kernel<CTC_EPI_F32><<<grid, block, 0, st>>>((const __nv_bfloat16*)A, lda,
+                                                                  (const __nv_bfloat16*)B, ldb, g);
+        CTC_LAUNCH_CHECK();
+        return 0;
+    }
+    // tile width: 128x256 tiles unless N only divides by 128 (e.g. the padded FF inner dim 1408)
+    const bool bn256 = (epi == CTC_EPI_ARGMAX) || (N % 256 == 0) || (N % 128 != 0);
+    const int BNsel = bn256 ? 256 : 128;
+    g.n_tiles_n = (N + BNsel - 1) / BNsel;
+    CUtensorMap ta, tb;
+    if (int e = make_tmap_bf16(&ta, A, M, K, lda, BM)) return e;
+    if (int e = make_tmap_bf16(&tb, B, N, K, ldb, BNsel)) return e;
+    switch (epi) {
+        case CTC_EPI_BF16:
+            return bn256 ? launch_tc<256, CTC_EPI_BF16>(ta, tb, g, st) : launch_tc<128, CTC_EPI_BF16>(ta, tb, g, st);
+        case CTC_EPI_F32:
+            return bn256 ? launch_tc<256, CTC_EPI_F32>(ta, tb, g, st) : launch_tc<128, CTC_EPI_F32>(ta, tb, g, st);
+        case CTC_EPI_ARGMAX:
+            CTC_REQUIRE(top2_val && top2_idx, "gemm: arg-max epilogue needs top2 buffers");
+            return launch_tc<256, CTC_EPI_ARGMAX>(ta, tb, g, st);
+        default:
+            CTC_REQUIRE(false, "gemm: unknown epilogue %d", epi);
+    }
+    return 0;
+}
+
+int gemm_argmax_tiles(int N) { return (N + 255) / 256; }
+
+}  // namespace ctc

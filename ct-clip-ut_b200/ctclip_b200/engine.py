@@ -1,0 +1,312 @@
+"""Kernel orchestration of the CTViT / CTCLIP image tower: forward and input-gradient backward.
+
+Mirrors, step by step, CTViT.forward (src/utils/ctvit.py:105-125), CTViT.encode (:88-103),
+Transformer.forward (src/utils/attention.py:322-336) and CTCLIP.forward (src/models/ctclip.py:99-129),
+but every step is one C-ABI call into the sm_100a library (see include/ctclip_b200.h).  torch is
+used for buffer allocation only.
+
+Row order: all token-space matrices are [R, C] with R = B*T*H*W in canonical (b, t, h, w) order —
+the spatial '(b t) (h w) d' view *is* this order and the temporal '(b h w) t d' view is addressed by
+stride inside the attention / PEG kernels (mode flag), so no rearrange is ever materialised.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BF16, EPI_F32, MODE_SPATIAL, MODE_TEMPORAL, call, stream_ptr
+from .plan import Config, LayerWeights, Plan
+
+LN_EPS = 1e-5
+
+
+@dataclass
+class LayerCtx:
+    x1: torch.Tensor = None      # fp32 stream after PEG (input of the attention LayerNorm)
+    x2: torch.Tensor = None      # fp32 stream after attention (input of the FF LayerNorm)
+    q: torch.Tensor = None       # bf16 [R, inner]
+    kv: torch.Tensor = None      # bf16 [R, 2*inner]
+    o: torch.Tensor = None       # bf16 [R, inner]
+    lse: torch.Tensor = None     # fp32 [R, heads]
+    u: torch.Tensor = None       # bf16 [R, 2*FP]  FF pre-activation
+
+
+@dataclass
+class Ctx:
+    """Everything the backward pass and the attribution methods need from one forward."""
+    B: int = 0
+    T: int = 0
+    volume: torch.Tensor = None
+    vol_stride: int = 0
+    alpha: Optional[torch.Tensor] = None
+    x_lin: torch.Tensor = None                 # patch-embedding Linear output (input of LayerNorm(dim))
+    x_in: torch.Tensor = None                  # tokens entering the spatial transformer
+    spatial: List[LayerCtx] = field(default_factory=list)
+    temporal: List[LayerCtx] = field(default_factory=list)
+    x_s_last: torch.Tensor = None              # stream leaving the last spatial layer (input of norm_out)
+    x_s_out: torch.Tensor = None               # spatial norm_out output = input of temporal layer 0
+    x_t_last: torch.Tensor = None
+    x_pre_vq: torch.Tensor = None              # temporal norm_out output (fp32)
+    indices: torch.Tensor = None               # int32 [R]
+    pooled: torch.Tensor = None                # fp32 [B, HW*C]
+    latent: torch.Tensor = None                # fp32 [B, NL] (un-normalised)
+    image_latents: torch.Tensor = None
+    sim: torch.Tensor = None                   # fp32 [B, Bt]
+    dlatent: torch.Tensor = None
+    tokens: Optional[torch.Tensor] = None      # fp32 [R, C] quantised tokens (optional)
+    # gradient captures for Grad-CAM (visualizations.py:140-218): grads of the residual stream
+    grads: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+
+class Engine:
+    def __init__(self, plan: Plan, gemm_impl: int = _lib.GEMM_TCGEN05):
+        self.plan = plan
+        self.cfg = plan.cfg
+        self.dev = plan.device
+        self.gemm_impl = gemm_impl
+
+    # ------------------------------------------------------------------ helpers
+    def _empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.dev)
+
+    def gemm(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, epi: int, bias=None, resid=None):
+        """out[M,N] = a[M,K] @ w[N,K]^T (+bias)(+resid)"""
+        M, K = a.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == N
+        call("ctc_gemm_bf16", a, a.stride(0), w, w.stride(0), out, out.stride(0), M, N, K, epi, bias, resid,
+             resid.stride(0) if resid is not None else 0, self.gemm_impl, stream_ptr())
+        return out
+
+    def layernorm(self, x, g, b, y_bf16=None, y_f32=None, xraw=None):
+        R, C = x.shape
+        call("ctc_layernorm_fwd", x, R, C, g, b, LN_EPS, y_bf16, y_f32, xraw, stream_ptr())
+
+    def layernorm_bwd(self, dy, x, g, out, accumulate, out_bf16=None):
+        R, C = x.shape
+        call("ctc_layernorm_bwd", dy, x, R, C, g, LN_EPS, out, int(accumulate), out_bf16, stream_ptr())
+
+    # ------------------------------------------------------------------ text tower tail
+    def text_latents(self, text_embeds: torch.Tensor) -> torch.Tensor:
+        """l2norm(to_text_latent(e)) — ctclip.py:115,119.  text_embeds fp32 [Bt, dim_text]."""
+        e = text_embeds.to(self.dev, torch.float32).contiguous()
+        out = self._empty(e.shape[0], self.cfg.dim_latent)
+        call("ctc_text_latent", e, self.plan.wt, e.shape[0], e.shape[1], self.cfg.dim_latent, out, stream_ptr())
+        return out
+
+    # ------------------------------------------------------------------ one transformer layer
+    def _layer_fwd(self, x0, lw: LayerWeights, B, T, mode, save: bool) -> Tuple[torch.Tensor, LayerCtx]:
+        cfg = self.cfg
+        R, C = x0.shape
+        H = W = cfg.hw
+        inner, FP = cfg.inner, cfg.ff_pad
+        bf = torch.bfloat16
+        lc = LayerCtx()
+        # x = peg(x) + x                                                   attention.py:325
+        x1 = self._empty(R, C)
+        call("ctc_peg", x0, B, T, H, W, C, lw.w27, lw.peg_bias, mode, 0, x1, None, stream_ptr())
+        # attention: q from LayerNorm(x), k/v from the RAW x                attention.py:138-142
+        xn, xraw = self._empty(R, C, dtype=bf), self._empty(R, C, dtype=bf)
+        self.layernorm(x1, lw.ln_g, lw.ln_b, y_bf16=xn, xraw=xraw)
+        q = self.gemm(xn, lw.wq, self._empty(R, inner, dtype=bf), EPI_BF16)
+        kv = self.gemm(xraw, lw.wkv, self._empty(R, 2 * inner, dtype=bf), EPI_BF16)
+        o, lse = self._empty(R, inner, dtype=bf), self._empty(R, cfg.heads)
+        call("ctc_attention_fwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, cfg.heads,
+             lw.q_scale, lw.k_scale, cfg.attn_scale, self.plan.bias_table if mode == MODE_SPATIAL else None, mode,
+             o, lse, stream_ptr())
+        # x = to_out(attn) + x                                             attention.py:182, 328
+        x2 = self.gemm(o, lw.wout, self._empty(R, C), EPI_F32, resid=x1)
+        # x = ff(x) + x                                                    attention.py:43-51, 334
+        xn2 = xn  # reuse
+        self.layernorm(x2, lw.ff_ln_w, lw.ff_ln_b, y_bf16=xn2)
+        u = self.gemm(xn2, lw.w1, self._empty(R, 2 * FP, dtype=bf), EPI_BF16)
+        hff = self._empty(R, FP, dtype=bf)
+        call("ctc_geglu_fwd", u, R, FP, hff, stream_ptr())
+        x3 = self.gemm(hff, lw.w2, self._empty(R, C), EPI_F32, resid=x2)
+        if save:
+            lc.x1, lc.x2, lc.q, lc.kv, lc.o, lc.lse, lc.u = x1, x2, q, kv, o, lse, u
+        return x3, lc
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, volume: torch.Tensor, text_latents: torch.Tensor, batch: Optional[int] = None,
+                alpha: Optional[torch.Tensor] = None, occl: Optional[torch.Tensor] = None,
+                occl_value: float = -1.0, save: bool = False, want_tokens: bool = False,
+                keep_attn: bool = False) -> Ctx:
+        """volume fp32 [Bv, 1, D, H, W] (Bv == batch, or Bv == 1 shared by all `batch` rows: windows /
+        alpha steps of one volume).  alpha fp32 [batch] (IG interpolation), occl int32 [batch, 6]
+        (occlusion cubes).  `save` keeps what backward needs; `keep_attn` keeps q/kv/lse only (rollout)."""
+        cfg, pl = self.cfg, self.plan
+        assert volume.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous()
+        Bv, _, D, Hv, Wv = volume.shape
+        B = batch or Bv
+        assert Bv in (1, B)
+        assert Hv == cfg.image_size and Wv == cfg.image_size
+        T, H = D // cfg.temporal_patch_size, cfg.hw
+        R, C, P = B * T * H * H, cfg.dim, cfg.patch_dim
+        bf = torch.bfloat16
+        ctx = Ctx(B=B, T=T, volume=volume, vol_stride=(D * Hv * Wv if Bv == B and B > 1 else 0), alpha=alpha)
+        keep = save or keep_attn
+
+        # to_patch_emb: patchify + LN(P) -> Linear(P, dim) + bias -> LN(dim)      ctvit.py:44-52
+        a_pe = self._empty(R, P, dtype=bf)
+        call("ctc_patchify_ln_fwd", volume, ctx.vol_stride, B, D, Hv, Wv, cfg.temporal_patch_size, cfg.patch_size,
+             pl.pe_ln1_w, pl.pe_ln1_b, LN_EPS, alpha, occl, occl_value, a_pe, stream_ptr())
+        x_lin = self.gemm(a_pe, pl.pe_w, self._empty(R, C), EPI_F32, bias=pl.pe_b)
+        del a_pe
+        x = self._empty(R, C)
+        self.layernorm(x_lin, pl.pe_ln2_w, pl.pe_ln2_b, y_f32=x)
+        if save:
+            ctx.x_lin, ctx.x_in = x_lin, x
+
+        # spatial transformer over '(b t) (h w) d'                               ctvit.py:94-96
+        for lw in pl.spatial:
+            x, lc = self._layer_fwd(x, lw, B, T, MODE_SPATIAL, keep)
+            ctx.spatial.append(lc)
+        xs = self._empty(R, C)
+        self.layernorm(x, pl.spatial_norm_g, pl.spatial_norm_b, y_f32=xs)
+        if save:
+            ctx.x_s_last, ctx.x_s_out = x, xs
+        x = xs
+        # temporal transformer over '(b h w) t d'                                ctvit.py:99-101
+        for lw in pl.temporal:
+            x, lc = self._layer_fwd(x, lw, B, T, MODE_TEMPORAL, keep)
+            ctx.temporal.append(lc)
+        xt, xt_bf = self._empty(R, C), self._empty(R, C, dtype=bf)
+        self.layernorm(x, pl.temporal_norm_g, pl.temporal_norm_b, y_f32=xt, y_bf16=xt_bf)
+        if save:
+            ctx.x_t_last = x
+        ctx.x_pre_vq = xt
+
+        # VQ (cosine codebook, arg-max)                                           ctvit.py:115-118
+        K = cfg.codebook_size
+        n_cand = ((K + 255) // 256) * 2
+        cand_val = self._empty(R, n_cand)
+        cand_idx = self._empty(R, n_cand, dtype=torch.int32)
+        ind = self._empty(R, dtype=torch.int32)
+        call("ctc_vq_argmax", xt, xt_bf, R, C, pl.codebook, pl.codebook_bf16, K, cand_val, cand_idx, ind, stream_ptr())
+        ctx.indices = ind
+        # tokens.mean(dim=1) -> view(B, -1) -> to_visual_latent -> l2norm -> sim   ctclip.py:110-127
+        HW = H * H
+        pooled = self._empty(B, HW * C)
+        tokens = self._empty(R, C) if want_tokens else None
+        call("ctc_vq_gather_pool", ind, pl.codebook, B, T, HW, C, pooled, None, tokens, stream_ptr())
+        ctx.pooled, ctx.tokens = pooled, tokens
+        L, NL = HW * C, cfg.dim_latent
+        n_chunks = (L + 1023) // 1024
+        partial = self._empty(n_chunks, B, NL)
+        latent = self._empty(B, NL)
+        call("ctc_latent_proj", pooled, pl.wv_bf16, B, L, NL, partial, n_chunks, latent, stream_ptr())
+        Bt = text_latents.shape[0]
+        sim, il = self._empty(B, Bt), self._empty(B, NL)
+        dlat = self._empty(B, NL) if save else None
+        call("ctc_latent_sim", latent, text_latents, B, Bt, NL, pl.temp_exp, sim, il, dlat, stream_ptr())
+        ctx.latent, ctx.image_latents, ctx.sim, ctx.dlatent = latent, il, sim, dlat
+        return ctx
+
+    # ------------------------------------------------------------------ backward
+    def _layer_bwd(self, dx3, dx3_bf, lc: LayerCtx, lw: LayerWeights, B, T, mode, capture: Optional[dict], tag: str):
+        """dx3: fp32 grad of the stream leaving the layer (overwritten), dx3_bf its bf16 copy.
+        Returns (dx0 fp32, dx0 bf16): grad of the stream entering the layer."""
+        cfg = self.cfg
+        R, C = dx3.shape
+        H = W = cfg.hw
+        inner, FP = cfg.inner, cfg.ff_pad
+        bf = torch.bfloat16
+        if capture is not None:
+            capture[tag + "_ff"] = dx3.clone()          # d/d(ff output)  == grad of x3
+        # ---- FeedForward
+        dh = self.gemm(dx3_bf, lw.w2_t, self._empty(R, FP, dtype=bf), EPI_BF16)
+        du = self._empty(R, 2 * FP, dtype=bf)
+        call("ctc_geglu_bwd", lc.u, dh, R, FP, du, stream_ptr())
+        del dh
+        dxn2 = self.gemm(du, lw.w1_t, self._empty(R, C), EPI_F32)
+        del du
+        dx2, dx2_bf = dx3, dx3_bf
+        self.layernorm_bwd(dxn2, lc.x2, lw.ff_ln_w, dx2, True, dx2_bf)
+        if capture is not None:
+            capture[tag + "_attn"] = dx2.clone()        # d/d(attention module output) == grad of x2
+        # ---- attention
+        d_o = self.gemm(dx2_bf, lw.wout_t, self._empty(R, inner, dtype=bf), EPI_BF16)
+        dq = self._empty(R, inner, dtype=bf)
+        dkv = self._empty(R, 2 * inner, dtype=bf)
+        delta = self._empty(R, cfg.heads)
+        call("ctc_attention_bwd", lc.q, inner, lc.kv, lc.kv.data_ptr() + inner * 2, 2 * inner, lc.o, d_o, lc.lse,
+             B, T, H, W, cfg.heads, lw.q_scale, lw.k_scale, cfg.attn_scale,
+             self.plan.bias_table if mode == MODE_SPATIAL else None, mode, dq, inner, dkv,
+             dkv.data_ptr() + inner * 2, 2 * inner, delta, stream_ptr())
+        dx1 = self.gemm(dkv, lw.wkv_t, dx2, EPI_F32, resid=dx2)           # k/v read the raw stream
+        dxn = self.gemm(dq, lw.wq_t, dxn2, EPI_F32)
+        self.layernorm_bwd(dxn, lc.x1, lw.ln_g, dx1, True, None)
+        # ---- PEG adjoint
+        dx0, dx0_bf = dxn, dx2_bf
+        call("ctc_peg", dx1, B, T, H, W, C, lw.w27, None, mode, 1, dx0, dx0_bf, stream_ptr())
+        return dx0, dx0_bf
+
+    def backward(self, ctx: Ctx, grad_out: Optional[torch.Tensor] = None, sum_over_batch: bool = False,
+                 capture_grads: bool = False, to_input: bool = True) -> Optional[torch.Tensor]:
+        """Input gradient of sum_b sim[b, b % Bt] (the `sim[rank, rank].backward()` of
+        visualizations.py:580,786,868,921) w.r.t. the (interpolated) voxels.
+        sum_over_batch: accumulate all batch rows into `grad_out` [D,H,W] (IG partial sum, +=).
+        capture_grads: keep the residual-stream gradients Grad-CAM reads."""
+        cfg, pl = self.cfg, self.plan
+        B, T = ctx.B, ctx.T
+        H = cfg.hw
+        HW, C = H * H, cfg.dim
+        R = B * T * HW
+        bf = torch.bfloat16
+        cap = ctx.grads if capture_grads else None
+        L, NL = HW * C, cfg.dim_latent
+        dpooled = self._empty(B, L)
+        call("ctc_latent_proj_bwd", ctx.dlatent, pl.wv_bf16, B, L, NL, dpooled, stream_ptr())
+        dxt = self._empty(R, C)
+        call("ctc_vq_bwd", dpooled, None, ctx.x_pre_vq, B, T, HW, C, 0 if cfg.vq_grad_mode == "ste_l2norm" else 1,
+             dxt, stream_ptr())
+        if cap is not None:
+            # gradient at the VQ output (visualizations.py:140-150): dtokens[b,t,hw,:] = dpooled[b,hw,:]/T
+            cap["vq"] = (dpooled.view(B, 1, HW, C) / T).expand(B, T, HW, C).reshape(R, C)
+        del dpooled
+        dx, dx_bf = self._empty(R, C), self._empty(R, C, dtype=bf)
+        self.layernorm_bwd(dxt, ctx.x_t_last, pl.temporal_norm_g, dx, False, dx_bf)
+        del dxt
+        for i in reversed(range(len(pl.temporal))):
+            dx, dx_bf = self._layer_bwd(dx, dx_bf, ctx.temporal[i], pl.temporal[i], B, T, MODE_TEMPORAL, cap,
+                                        f"temporal{i}")
+        d2, d2_bf = self._empty(R, C), dx_bf
+        self.layernorm_bwd(dx, ctx.x_s_last, pl.spatial_norm_g, d2, False, d2_bf)
+        dx, dx_bf = d2, d2_bf
+        for i in reversed(range(len(pl.spatial))):
+            dx, dx_bf = self._layer_bwd(dx, dx_bf, ctx.spatial[i], pl.spatial[i], B, T, MODE_SPATIAL, cap,
+                                        f"spatial{i}")
+        if not to_input:
+            return None
+        # patch embedding adjoint
+        dlin, dlin_bf = self._empty(R, C), dx_bf
+        self.layernorm_bwd(dx, ctx.x_lin, pl.pe_ln2_w, dlin, False, dlin_bf)
+        da = self.gemm(dlin_bf, pl.pe_w_t, self._empty(R, cfg.patch_dim, dtype=bf), EPI_BF16)
+        _, _, D, Hv, Wv = ctx.volume.shape
+        if grad_out is None:
+            grad_out = (torch.zeros(D, Hv, Wv, device=self.dev) if sum_over_batch
+                        else self._empty(B, 1, D, Hv, Wv))
+        call("ctc_patchify_ln_bwd", ctx.volume, ctx.vol_stride, B, D, Hv, Wv, cfg.temporal_patch_size, cfg.patch_size,
+             pl.pe_ln1_w, LN_EPS, ctx.alpha, da, grad_out, int(sum_over_batch), 1.0, stream_ptr())
+        return grad_out
+
+    # ------------------------------------------------------------------ attention probabilities
+    def attention_probs(self, ctx: Ctx, kind: str, layer: int) -> torch.Tensor:
+        """Materialise what Attention.forward returns as `attn` (attention.py:174): spatial ->
+        [B*T, heads, HW, HW], temporal -> [B*HW, heads, T, T] (fp32)."""
+        cfg = self.cfg
+        H = cfg.hw
+        spatial = kind == "spatial"
+        lc = (ctx.spatial if spatial else ctx.temporal)[layer]
+        lw = (self.plan.spatial if spatial else self.plan.temporal)[layer]
+        n = H * H if spatial else ctx.T
+        n_seq = ctx.B * ctx.T if spatial else ctx.B * H * H
+        probs = self._empty(n_seq, cfg.heads, n, n)
+        call("ctc_attention_probs", lc.q, cfg.inner, lc.kv, 2 * cfg.inner, lc.lse, ctx.B, ctx.T, H, H, cfg.heads,
+             lw.q_scale, lw.k_scale, cfg.attn_scale, self.plan.bias_table if spatial else None,
+             MODE_SPATIAL if spatial else MODE_TEMPORAL, probs, stream_ptr())
+        return probs

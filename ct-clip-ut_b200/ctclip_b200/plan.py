@@ -1,0 +1,134 @@
+"""Weight plan: the reference state dict (keys of SURVEY §8b) repacked once for the sm_100a kernels.
+
+Only layout work happens here (casts to bf16, transposes for the input-gradient GEMMs, zero padding
+of the 1365-wide FeedForward inner dimension to a TMA-legal 1408, the 27-tap depthwise weights as
+[27, C]); the one piece of arithmetic — the continuous-position-bias MLP, which the reference
+re-evaluates for all 576² pairs on every forward (attention.py:259-277) — is evaluated once for the
+47² distinct offsets by the `ctc_cpb_table` kernel.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class Config:
+    """Hyper-parameters of CTViT / CTCLIP (src/inference_ctclip.py:21-39)."""
+    dim: int = 512
+    codebook_size: int = 8192
+    image_size: int = 480
+    patch_size: int = 20
+    temporal_patch_size: int = 10
+    spatial_depth: int = 4
+    temporal_depth: int = 4
+    dim_head: int = 32
+    heads: int = 8
+    dim_text: int = 768
+    dim_latent: int = 512
+    attn_scale: float = 8.0
+    vq_grad_mode: str = "ste_l2norm"
+
+    @property
+    def hw(self) -> int:
+        return self.image_size // self.patch_size
+
+    @property
+    def patch_dim(self) -> int:
+        return self.temporal_patch_size * self.patch_size ** 2
+
+    @property
+    def ff_inner(self) -> int:
+        return int(4 * (2 / 3) * self.dim)          # attention.py:43
+
+    @property
+    def ff_pad(self) -> int:
+        return (self.ff_inner + 127) // 128 * 128    # 1365 -> 1408: 16-byte rows for TMA, 128-wide tiles
+
+    @property
+    def inner(self) -> int:
+        return self.dim_head * self.heads
+
+
+class LayerWeights:
+    __slots__ = ("w27", "peg_bias", "ln_g", "ln_b", "q_scale", "k_scale", "wq", "wkv", "wout", "wq_t", "wkv_t",
+                 "wout_t", "ff_ln_w", "ff_ln_b", "w1", "w2", "w1_t", "w2_t")
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).contiguous()
+
+
+class Plan:
+    """Device-resident, kernel-ready weights."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Config, device: Optional[torch.device] = None):
+        _lib.require_device()
+        if cfg.dim_head != 32:
+            raise RuntimeError("ctclip_b200: the attention kernels are specialised for dim_head == 32 "
+                               "(src/inference_ctclip.py:29)")
+        self.cfg = cfg
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        sd = {k: v.detach().to(dev) for k, v in state_dict.items() if isinstance(v, torch.Tensor)}
+        f32 = lambda k: sd[k].float().contiguous()
+        vt = "visual_transformer."
+        C, F, FP = cfg.dim, cfg.ff_inner, cfg.ff_pad
+
+        # patch embedding (ctvit.py:44-52)
+        self.pe_ln1_w, self.pe_ln1_b = f32(vt + "to_patch_emb.1.weight"), f32(vt + "to_patch_emb.1.bias")
+        w = f32(vt + "to_patch_emb.2.weight")                      # [C, P]
+        self.pe_w, self.pe_w_t = _bf16(w), _bf16(w.t())
+        self.pe_b = f32(vt + "to_patch_emb.2.bias")
+        self.pe_ln2_w, self.pe_ln2_b = f32(vt + "to_patch_emb.3.weight"), f32(vt + "to_patch_emb.3.bias")
+
+        # continuous position bias table [heads, (2H-1)(2W-1)]
+        p = vt + "spatial_rel_pos_bias.net."
+        hw = cfg.hw
+        self.bias_table = torch.empty(cfg.heads, (2 * hw - 1) ** 2, device=dev, dtype=torch.float32)
+        _lib.call("ctc_cpb_table", f32(p + "0.0.weight"), f32(p + "0.0.bias"), f32(p + "1.0.weight"),
+                  f32(p + "1.0.bias"), f32(p + "2.weight"), f32(p + "2.bias"), C, cfg.heads, hw, hw,
+                  self.bias_table, _lib.stream_ptr())
+
+        self.spatial = [self._layer(sd, f"{vt}enc_spatial_transformer.layers.{i}.") for i in range(cfg.spatial_depth)]
+        self.temporal = [self._layer(sd, f"{vt}enc_temporal_transformer.layers.{i}.") for i in range(cfg.temporal_depth)]
+        self.spatial_norm_g = f32(vt + "enc_spatial_transformer.norm_out.gamma")
+        self.spatial_norm_b = f32(vt + "enc_spatial_transformer.norm_out.beta")
+        self.temporal_norm_g = f32(vt + "enc_temporal_transformer.norm_out.gamma")
+        self.temporal_norm_b = f32(vt + "enc_temporal_transformer.norm_out.beta")
+
+        cb = f32(vt + "vq._codebook.embed")[0].contiguous()       # [K, C]
+        self.codebook, self.codebook_bf16 = cb, _bf16(cb)
+
+        self.wv_bf16 = _bf16(f32("to_visual_latent.weight"))       # [NL, L]
+        self.wt = f32("to_text_latent.weight")                     # [NL, DT]
+        self.temp_exp = float(sd["temperature"].float().exp())
+        torch.cuda.synchronize(dev)
+
+    def _layer(self, sd, p: str) -> LayerWeights:
+        cfg = self.cfg
+        C, F, FP = cfg.dim, cfg.ff_inner, cfg.ff_pad
+        f32 = lambda k: sd[p + k].float().contiguous()
+        lw = LayerWeights()
+        lw.w27 = f32("0.dsconv.weight").reshape(C, 27).t().contiguous()      # [27, C], tap = (a*3+b)*3+c
+        lw.peg_bias = f32("0.dsconv.bias")
+        lw.ln_g, lw.ln_b = f32("1.norm.gamma"), f32("1.norm.beta")
+        lw.q_scale, lw.k_scale = f32("1.q_scale"), f32("1.k_scale")
+        wq, wkv, wout = f32("1.to_q.weight"), f32("1.to_kv.weight"), f32("1.to_out.weight")
+        lw.wq, lw.wkv, lw.wout = _bf16(wq), _bf16(wkv), _bf16(wout)
+        lw.wq_t, lw.wkv_t, lw.wout_t = _bf16(wq.t()), _bf16(wkv.t()), _bf16(wout.t())
+        lw.ff_ln_w, lw.ff_ln_b = f32("3.0.weight"), f32("3.0.bias")
+        w1, w2 = f32("3.1.weight"), f32("3.4.weight")                          # [2F, C], [C, F]
+        w1p = torch.zeros(2 * FP, C, device=w1.device)
+        w1p[:F] = w1[:F]                 # GEGLU value half  (attention.py:40: x, gate = chunk(2))
+        w1p[FP:FP + F] = w1[F:]          # GEGLU gate half
+        w2p = torch.zeros(C, FP, device=w2.device)
+        w2p[:, :F] = w2
+        lw.w1, lw.w2 = _bf16(w1p), _bf16(w2p)
+        lw.w1_t, lw.w2_t = _bf16(w1p.t()), _bf16(w2p.t())
+        return lw

