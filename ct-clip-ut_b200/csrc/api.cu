@@ -13,11 +13,14 @@ void set_last_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
 }  // namespace ctc
 
 using namespace ctc;
 
 extern "C" int ctc_version(void) { return CTC_VERSION; }
+extern "C" long long ctc_launch_count(void) { return g_launches; }
 extern "C" const char* ctc_last_error(void) { return g_err; }
 
 extern "C" int ctc_device_check(void) {

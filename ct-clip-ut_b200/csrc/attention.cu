@@ -23,8 +23,11 @@
 namespace ctc {
 
 static constexpr int DH = 32;          // head dim (fixed on this path: inference_ctclip.py:29)
-static constexpr int QB = 64;          // query rows (or key rows in dKV) per CTA
-static constexpr int KB = 64;          // keys per online-softmax step
+// Tile configurations <QB rows per (CTA, head), KBLK keys per softmax step, HPC heads per CTA>:
+//   spatial  (n = 576): one head per CTA, large row tiles so that 12 (fwd) / 6 (bwd) warps share one
+//                       resident K/V copy (occupancy is bounded by the 72 KB K/V tile, not by threads);
+//   temporal (n = 24) : all 8 heads of one (b,h,w) column in one CTA, 32-row tiles, so that the strided
+//                       token rows (q 512 B, kv 1 KB) are each fetched once, fully coalesced.
 static constexpr float LOG2E = 1.4426950408889634f;
 static constexpr float LN2 = 0.6931471805599453f;
 
@@ -49,16 +52,18 @@ CTC_DEVINL long long seq_row(const AttnParams& p, int s, int i) {
 // 64-byte rows (32 bf16), 16-byte chunks XOR-swizzled so that ldmatrix is bank-conflict free
 CTC_DEVINL uint32_t tile_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
-// Load `rows` rows of 32 bf16 (row i of the sequence at src + seq_row*ld + head*32) into a swizzled tile.
-// NORM: l2-normalise and multiply by vec[d] * mul (fp32 math).  Rows >= n are zero-filled.
+// Load `rows` rows of 32 bf16 for each of `hpc` heads (row i of the sequence at src + seq_row*ld + head*32) into
+// per-head swizzled tiles (tile + hl*tile_stride).  NORM: l2-normalise and multiply by vec[d] * mul (fp32).
+// Rows >= n are zero-filled.
 template <bool NORM>
-CTC_DEVINL void load_tile(uint8_t* tile, const __nv_bfloat16* src, long long ld, const AttnParams& p, int s, int head,
-                          int row0, int rows, const float* vec, float mul) {
-    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+CTC_DEVINL void load_tile(uint8_t* tile, int tile_stride, const __nv_bfloat16* src, long long ld, const AttnParams& p,
+                          int s, int head0, int hpc, int row0, int rows, const float* vec, float mul) {
+    for (int idx = threadIdx.x; idx < rows * hpc; idx += blockDim.x) {
+        const int r = idx / hpc, hl = idx - r * hpc;       // consecutive threads -> consecutive heads of one row
         const int i = row0 + r;
         uint4 c[4];
         if (i < p.n) {
-            const uint4* g = reinterpret_cast<const uint4*>(src + seq_row(p, s, i) * ld + head * DH);
+            const uint4* g = reinterpret_cast<const uint4*>(src + seq_row(p, s, i) * ld + (head0 + hl) * DH);
 #pragma unroll
             for (int j = 0; j < 4; ++j) c[j] = g[j];
             if (NORM) {
@@ -87,8 +92,9 @@ CTC_DEVINL void load_tile(uint8_t* tile, const __nv_bfloat16* src, long long ld,
 #pragma unroll
             for (int j = 0; j < 4; ++j) c[j] = make_uint4(0, 0, 0, 0);
         }
+        uint8_t* t = tile + (long long)hl * tile_stride;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(tile + tile_off(r, j)) = c[j];
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(t + tile_off(r, j)) = c[j];
     }
 }
 
@@ -118,7 +124,7 @@ CTC_DEVINL void mma_colsB(float (&acc)[4][4], const uint32_t (&a)[4], uint32_t t
 }
 
 
-// common prologue: q/k scale vectors, bias table (pre-multiplied by log2e), key index table
+// common prologue: bias table (pre-multiplied by log2e) and key index table
 CTC_DEVINL void load_bias(const AttnParams& p, int head, float* bias, int* tab, int count) {
     if (p.bias_table) {
         const int nb = (2 * p.H - 1) * (2 * p.W - 1);
@@ -130,45 +136,67 @@ CTC_DEVINL void load_bias(const AttnParams& p, int head, float* bias, int* tab, 
         }
     }
 }
+CTC_DEVINL int bias_base(const AttnParams& p, int i) {
+    const int ii = min(i, p.n - 1);
+    return (ii / p.W + p.H - 1) * (2 * p.W - 1) + (ii % p.W + p.W - 1);
+}
+
+// S tile (16 rows x KBLK keys) = A(16 x 32) * rows-of-B^T (+ bias) in the log2 domain
+template <int KBLK>
+CTC_DEVINL void score_tile(float (&sc)[KBLK / 8][4], const uint32_t (&a)[2][4], uint32_t b_addr, int k0, int lane,
+                           const float* bias, const int* tabj, int base0, int base1, bool has_bias) {
+    const int t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < KBLK / 8; ++nt) {
+        sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+        mma_rowsB(sc[nt], a, b_addr, k0 + nt * 8, lane);
+        if (has_bias) {
+            const int j = k0 + nt * 8 + 2 * t;
+            const int tj0 = tabj[j], tj1 = tabj[j + 1];
+            sc[nt][0] += bias[base0 - tj0]; sc[nt][1] += bias[base0 - tj1];
+            sc[nt][2] += bias[base1 - tj0]; sc[nt][3] += bias[base1 - tj1];
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward (PROBS=false) / probability materialisation (PROBS=true)
 // ---------------------------------------------------------------------------------------------
-template <bool PROBS>
-__global__ void __launch_bounds__(128)
+template <int QB, int KBLK, int HPC, bool PROBS>
+__global__ void __launch_bounds__(HPC * (QB / 16) * 32, (HPC * (QB / 16) * 32 <= 384) ? 2 : 1)
 attn_fwd_kernel(const AttnParams p) {
     extern __shared__ __align__(128) uint8_t sm[];
-    const int qb = blockIdx.z, head = blockIdx.y, s = blockIdx.x;
+    constexpr int WPH = QB / 16;
+    const int qb = blockIdx.z, head0 = blockIdx.y * HPC, s = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* ks = sm;
-    uint8_t* vs = ks + p.n_pad * 64;
-    uint8_t* qs = vs + p.n_pad * 64;
-    float* sv = reinterpret_cast<float*>(qs + QB * 64);   // 64 floats: q_scale, k_scale
+    const int hl = warp / WPH, wq = warp % WPH, head = head0 + hl;
+    const int kv_bytes = p.n_pad * 64;
+    uint8_t* ks = sm;                                   // [HPC][n_pad][64 B]
+    uint8_t* vs = ks + HPC * kv_bytes;
+    uint8_t* qs = vs + HPC * kv_bytes;                  // [HPC][QB][64 B]
+    float* sv = reinterpret_cast<float*>(qs + HPC * QB * 64);   // q_scale[32], k_scale[32]
     int* tabj = reinterpret_cast<int*>(sv + 64);
     float* bias = reinterpret_cast<float*>(tabj + p.n_pad);
     if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
     else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
-    load_bias(p, head, bias, tabj, p.n_pad);
+    load_bias(p, head0, bias, tabj, p.n_pad);
     __syncthreads();
-    load_tile<true>(ks, p.k, p.ldkv, p, s, head, 0, p.n_pad, sv + 32, 1.0f);
-    if (!PROBS) load_tile<false>(vs, p.v, p.ldkv, p, s, head, 0, p.n_pad, nullptr, 1.0f);
-    load_tile<true>(qs, p.q, p.ldq, p, s, head, qb * QB, QB, sv, p.scale * LOG2E);
+    load_tile<true>(ks, kv_bytes, p.k, p.ldkv, p, s, head0, HPC, 0, p.n_pad, sv + 32, 1.0f);
+    if (!PROBS) load_tile<false>(vs, kv_bytes, p.v, p.ldkv, p, s, head0, HPC, 0, p.n_pad, nullptr, 1.0f);
+    load_tile<true>(qs, QB * 64, p.q, p.ldq, p, s, head0, HPC, qb * QB, QB, sv, p.scale * LOG2E);
     __syncthreads();
 
-    const int row_base = qb * QB + warp * 16;
+    const int row_base = qb * QB + wq * 16;
     if (row_base >= p.n) return;
-    const uint32_t ks_a = smem_u32(ks), vs_a = smem_u32(vs), qs_a = smem_u32(qs);
+    const uint32_t ks_a = smem_u32(ks + hl * kv_bytes), vs_a = smem_u32(vs + hl * kv_bytes);
+    const uint32_t qs_a = smem_u32(qs + hl * QB * 64);
     uint32_t aq[2][4];
-    load_a_frags(aq, qs_a, warp * 16, lane);
+    load_a_frags(aq, qs_a, wq * 16, lane);
     const int g = lane >> 2, t = lane & 3;
     const int i0 = row_base + g, i1 = i0 + 8;
-    const int nW = 2 * p.W - 1;
     const bool has_bias = p.bias_table != nullptr;
-    int base0 = 0, base1 = 0;
-    if (has_bias) {
-        base0 = (min(i0, p.n - 1) / p.W + p.H - 1) * nW + (min(i0, p.n - 1) % p.W + p.W - 1);
-        base1 = (min(i1, p.n - 1) / p.W + p.H - 1) * nW + (min(i1, p.n - 1) % p.W + p.W - 1);
-    }
+    const int base0 = has_bias ? bias_base(p, i0) : 0, base1 = has_bias ? bias_base(p, i1) : 0;
+    const bool need_mask = (p.n % KBLK) != 0;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float oacc[4][4];
 #pragma unroll
@@ -181,25 +209,21 @@ attn_fwd_kernel(const AttnParams p) {
         lse2_1 = (i1 < p.n) ? p.lse[seq_row(p, s, i1) * p.heads + head] * LOG2E : 0.f;
     }
 
-    for (int kb = 0; kb < p.n_pad / KB; ++kb) {
-        float sc[8][4];
+    for (int kb = 0; kb < p.n_pad / KBLK; ++kb) {
+        float sc[KBLK / 8][4];
+        score_tile<KBLK>(sc, aq, ks_a, kb * KBLK, lane, bias, tabj, base0, base1, has_bias);
+        if (need_mask) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-            mma_rowsB(sc[nt], aq, ks_a, kb * KB + nt * 8, lane);
-            const int j = kb * KB + nt * 8 + 2 * t;
-            if (has_bias) {
-                const int tj0 = tabj[j], tj1 = tabj[j + 1];
-                sc[nt][0] += bias[base0 - tj0]; sc[nt][1] += bias[base0 - tj1];
-                sc[nt][2] += bias[base1 - tj0]; sc[nt][3] += bias[base1 - tj1];
+            for (int nt = 0; nt < KBLK / 8; ++nt) {
+                const int j = kb * KBLK + nt * 8 + 2 * t;
+                if (j >= p.n) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
+                if (j + 1 >= p.n) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
             }
-            if (j >= p.n) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
-            if (j + 1 >= p.n) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
         }
         if (PROBS) {
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const int j = kb * KB + nt * 8 + 2 * t;
+            for (int nt = 0; nt < KBLK / 8; ++nt) {
+                const int j = kb * KBLK + nt * 8 + 2 * t;
                 if (i0 < p.n) {
                     float* pr = p.probs + (((long long)s * p.heads + head) * p.n + i0) * p.n + j;
                     if (j < p.n) pr[0] = exp2f(sc[nt][0] - lse2_0);
@@ -216,7 +240,7 @@ attn_fwd_kernel(const AttnParams p) {
         // online softmax (log2 domain)
         float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < KBLK / 8; ++nt) {
             bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
             bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
         }
@@ -227,7 +251,7 @@ attn_fwd_kernel(const AttnParams p) {
         m0 = nm0; m1 = nm1;
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < KBLK / 8; ++nt) {
             sc[nt][0] = exp2f(sc[nt][0] - m0); sc[nt][1] = exp2f(sc[nt][1] - m0);
             sc[nt][2] = exp2f(sc[nt][2] - m1); sc[nt][3] = exp2f(sc[nt][3] - m1);
             rs0 += sc[nt][0] + sc[nt][1]; rs1 += sc[nt][2] + sc[nt][3];
@@ -236,13 +260,13 @@ attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
         for (int a = 0; a < 4; ++a) { oacc[a][0] *= c0; oacc[a][1] *= c0; oacc[a][2] *= c1; oacc[a][3] *= c1; }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < KBLK / 16; ++kk) {
             uint32_t a[4];
             a[0] = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]);
             a[1] = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
             a[2] = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
             a[3] = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
-            mma_colsB(oacc, a, vs_a, kb * KB + kk * 16, lane);
+            mma_colsB(oacc, a, vs_a, kb * KBLK + kk * 16, lane);
         }
     }
     if (PROBS) return;
@@ -268,8 +292,8 @@ attn_fwd_kernel(const AttnParams p) {
 }
 
 // adjoint of x^ = l2norm(x) * vec for one row held in mma C layout (quad of lanes owns the row):
-// gacc = gradient w.r.t. (x^ / mul'), i.e. caller passes g already multiplied by everything but vec.
-// Returns dx for the 8 elements this thread owns (cols a*8 + 2t, +1 for a = 0..3).
+// g = gradient w.r.t. x^ (before the vec factor is applied here).  Returns dx for the 8 elements this
+// thread owns (cols a*8 + 2t, +1 for a = 0..3).
 CTC_DEVINL void l2norm_adjoint_row(const __nv_bfloat16* xrow, const float* vec, int t, float (&g)[8], float (&dx)[8]) {
     float x[8];
     float ss = 0.f;
@@ -294,37 +318,42 @@ CTC_DEVINL void l2norm_adjoint_row(const __nv_bfloat16* xrow, const float* vec, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, dQ: one CTA per (64-query block, head, sequence)
+// backward, dQ: one CTA per (QB-query block, head group, sequence)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+template <int QB, int KBLK, int HPC>
+__global__ void __launch_bounds__(HPC * (QB / 16) * 32, (HPC * (QB / 16) * 32 <= 256) ? 2 : 1)
 attn_bwd_dq_kernel(const AttnParams p) {
     extern __shared__ __align__(128) uint8_t sm[];
-    const int qb = blockIdx.z, head = blockIdx.y, s = blockIdx.x;
+    constexpr int WPH = QB / 16;
+    const int qb = blockIdx.z, head0 = blockIdx.y * HPC, s = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hl = warp / WPH, wq = warp % WPH, head = head0 + hl;
+    const int kv_bytes = p.n_pad * 64;
     uint8_t* ks = sm;
-    uint8_t* vs = ks + p.n_pad * 64;
-    uint8_t* qs = vs + p.n_pad * 64;
-    uint8_t* dos = qs + QB * 64;
-    float* sv = reinterpret_cast<float*>(dos + QB * 64);
-    float* dl = sv + 64;                                   // D for the 64 rows
-    int* tabj = reinterpret_cast<int*>(dl + QB);
+    uint8_t* vs = ks + HPC * kv_bytes;
+    uint8_t* qs = vs + HPC * kv_bytes;
+    uint8_t* dos = qs + HPC * QB * 64;
+    float* sv = reinterpret_cast<float*>(dos + HPC * QB * 64);
+    float* dl = sv + 64;                                   // D for the HPC*QB rows
+    int* tabj = reinterpret_cast<int*>(dl + HPC * QB);
     float* bias = reinterpret_cast<float*>(tabj + p.n_pad);
     if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
     else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
-    load_bias(p, head, bias, tabj, p.n_pad);
+    load_bias(p, head0, bias, tabj, p.n_pad);
     __syncthreads();
-    load_tile<true>(ks, p.k, p.ldkv, p, s, head, 0, p.n_pad, sv + 32, 1.0f);
-    load_tile<false>(vs, p.v, p.ldkv, p, s, head, 0, p.n_pad, nullptr, 1.0f);
-    load_tile<true>(qs, p.q, p.ldq, p, s, head, qb * QB, QB, sv, p.scale * LOG2E);
-    load_tile<false>(dos, p.d_o, (long long)p.heads * DH, p, s, head, qb * QB, QB, nullptr, 1.0f);
-    // D_i = sum_d dO_i,d * O_i,d   (thread per row)
-    if (threadIdx.x < QB) {
-        const int i = qb * QB + threadIdx.x;
+    load_tile<true>(ks, kv_bytes, p.k, p.ldkv, p, s, head0, HPC, 0, p.n_pad, sv + 32, 1.0f);
+    load_tile<false>(vs, kv_bytes, p.v, p.ldkv, p, s, head0, HPC, 0, p.n_pad, nullptr, 1.0f);
+    load_tile<true>(qs, QB * 64, p.q, p.ldq, p, s, head0, HPC, qb * QB, QB, sv, p.scale * LOG2E);
+    load_tile<false>(dos, QB * 64, p.d_o, (long long)p.heads * DH, p, s, head0, HPC, qb * QB, QB, nullptr, 1.0f);
+    // D_i = sum_d dO_i,d * O_i,d   (thread per (row, head))
+    for (int idx = threadIdx.x; idx < QB * HPC; idx += blockDim.x) {
+        const int r_ = idx / HPC, h_ = idx - r_ * HPC;
+        const int i = qb * QB + r_;
         float d = 0.f;
         if (i < p.n) {
             const long long r = seq_row(p, s, i);
-            const uint4* go = reinterpret_cast<const uint4*>(p.o + r * (p.heads * DH) + head * DH);
-            const uint4* gd = reinterpret_cast<const uint4*>(p.d_o + r * (p.heads * DH) + head * DH);
+            const uint4* go = reinterpret_cast<const uint4*>(p.o + r * (p.heads * DH) + (head0 + h_) * DH);
+            const uint4* gd = reinterpret_cast<const uint4*>(p.d_o + r * (p.heads * DH) + (head0 + h_) * DH);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint4 a = go[j], b = gd[j];
@@ -335,65 +364,58 @@ attn_bwd_dq_kernel(const AttnParams p) {
                     d += x.x * y.x + x.y * y.y;
                 }
             }
-            p.delta[r * p.heads + head] = d;
+            p.delta[r * p.heads + head0 + h_] = d;
         }
-        dl[threadIdx.x] = d;
+        dl[h_ * QB + r_] = d;
     }
     __syncthreads();
 
-    const int row_base = qb * QB + warp * 16;
+    const int row_base = qb * QB + wq * 16;
     if (row_base >= p.n) return;
-    const uint32_t ks_a = smem_u32(ks), vs_a = smem_u32(vs), qs_a = smem_u32(qs), dos_a = smem_u32(dos);
+    const uint32_t ks_a = smem_u32(ks + hl * kv_bytes), vs_a = smem_u32(vs + hl * kv_bytes);
+    const uint32_t qs_a = smem_u32(qs + hl * QB * 64), dos_a = smem_u32(dos + hl * QB * 64);
     uint32_t aq[2][4], ado[2][4];
-    load_a_frags(aq, qs_a, warp * 16, lane);
-    load_a_frags(ado, dos_a, warp * 16, lane);
+    load_a_frags(aq, qs_a, wq * 16, lane);
+    load_a_frags(ado, dos_a, wq * 16, lane);
     const int g = lane >> 2, t = lane & 3;
     const int i0 = row_base + g, i1 = i0 + 8;
-    const int nW = 2 * p.W - 1;
     const bool has_bias = p.bias_table != nullptr;
-    int base0 = 0, base1 = 0;
-    if (has_bias) {
-        base0 = (min(i0, p.n - 1) / p.W + p.H - 1) * nW + (min(i0, p.n - 1) % p.W + p.W - 1);
-        base1 = (min(i1, p.n - 1) / p.W + p.H - 1) * nW + (min(i1, p.n - 1) % p.W + p.W - 1);
-    }
+    const int base0 = has_bias ? bias_base(p, i0) : 0, base1 = has_bias ? bias_base(p, i1) : 0;
+    const bool need_mask = (p.n % KBLK) != 0;
     const float lse2_0 = (i0 < p.n) ? p.lse[seq_row(p, s, i0) * p.heads + head] * LOG2E : INFINITY;
     const float lse2_1 = (i1 < p.n) ? p.lse[seq_row(p, s, i1) * p.heads + head] * LOG2E : INFINITY;
-    const float d0 = dl[warp * 16 + g], d1 = dl[warp * 16 + g + 8];
+    const float d0 = dl[hl * QB + wq * 16 + g], d1 = dl[hl * QB + wq * 16 + g + 8];
     float dq[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) dq[a][b] = 0.f;
 
-    for (int kb = 0; kb < p.n_pad / KB; ++kb) {
-        float sc[8][4];
+    for (int kb = 0; kb < p.n_pad / KBLK; ++kb) {
+        float sc[KBLK / 8][4];
+        score_tile<KBLK>(sc, aq, ks_a, kb * KBLK, lane, bias, tabj, base0, base1, has_bias);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-            mma_rowsB(sc[nt], aq, ks_a, kb * KB + nt * 8, lane);
-            const int j = kb * KB + nt * 8 + 2 * t;
-            if (has_bias) {
-                const int tj0 = tabj[j], tj1 = tabj[j + 1];
-                sc[nt][0] += bias[base0 - tj0]; sc[nt][1] += bias[base0 - tj1];
-                sc[nt][2] += bias[base1 - tj0]; sc[nt][3] += bias[base1 - tj1];
-            }
+        for (int nt = 0; nt < KBLK / 8; ++nt) {
             float dp[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_rowsB(dp, ado, vs_a, kb * KB + nt * 8, lane);
-            const float p0 = (j < p.n) ? exp2f(sc[nt][0] - lse2_0) : 0.f;
-            const float p1 = (j + 1 < p.n) ? exp2f(sc[nt][1] - lse2_0) : 0.f;
-            const float p2 = (j < p.n) ? exp2f(sc[nt][2] - lse2_1) : 0.f;
-            const float p3 = (j + 1 < p.n) ? exp2f(sc[nt][3] - lse2_1) : 0.f;
+            mma_rowsB(dp, ado, vs_a, kb * KBLK + nt * 8, lane);
+            float p0 = exp2f(sc[nt][0] - lse2_0), p1 = exp2f(sc[nt][1] - lse2_0);
+            float p2 = exp2f(sc[nt][2] - lse2_1), p3 = exp2f(sc[nt][3] - lse2_1);
+            if (need_mask) {
+                const int j = kb * KBLK + nt * 8 + 2 * t;
+                if (j >= p.n) { p0 = 0.f; p2 = 0.f; }
+                if (j + 1 >= p.n) { p1 = 0.f; p3 = 0.f; }
+            }
             sc[nt][0] = p0 * (dp[0] - d0); sc[nt][1] = p1 * (dp[1] - d0);
             sc[nt][2] = p2 * (dp[2] - d1); sc[nt][3] = p3 * (dp[3] - d1);
         }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < KBLK / 16; ++kk) {
             uint32_t a[4];
             a[0] = pack_bf16(sc[2 * kk][0], sc[2 * kk][1]);
             a[1] = pack_bf16(sc[2 * kk][2], sc[2 * kk][3]);
             a[2] = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
             a[3] = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
-            mma_colsB(dq, a, ks_a, kb * KB + kk * 16, lane);
+            mma_colsB(dq, a, ks_a, kb * KBLK + kk * 16, lane);
         }
     }
     // dq^ -> dq through l2norm and q_scale; ds/dq^_d = scale * q_scale_d * k^_d  (k^ includes k_scale)
@@ -414,21 +436,26 @@ attn_bwd_dq_kernel(const AttnParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, dK/dV: one CTA per (64-key block, head, sequence); queries are the reduction axis
+// backward, dK/dV: one CTA per (QB-key block, head group, sequence); queries are the reduction axis,
+// walked in blocks of KBLK.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+template <int QB, int KBLK, int HPC>
+__global__ void __launch_bounds__(HPC * (QB / 16) * 32, (HPC * (QB / 16) * 32 <= 192) ? 2 : 1)
 attn_bwd_dkv_kernel(const AttnParams p) {
     extern __shared__ __align__(128) uint8_t sm[];
-    const int kblk = blockIdx.z, head = blockIdx.y, s = blockIdx.x;
+    constexpr int WPH = QB / 16;
+    const int kblk = blockIdx.z, head0 = blockIdx.y * HPC, s = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* qs = sm;                                       // all queries (scaled q^)
-    uint8_t* dos = qs + p.n_pad * 64;                       // all dO rows
-    uint8_t* ks = dos + p.n_pad * 64;                       // my 64 keys (k^)
-    uint8_t* vs = ks + QB * 64;                             // my 64 values
-    float* sv = reinterpret_cast<float*>(vs + QB * 64);
-    float* lse2 = sv + 64;                                  // [n_pad]
-    float* dl = lse2 + p.n_pad;                             // [n_pad]
-    int* basei = reinterpret_cast<int*>(dl + p.n_pad);      // [n_pad]
+    const int hl = warp / WPH, wq = warp % WPH, head = head0 + hl;
+    const int kv_bytes = p.n_pad * 64;
+    uint8_t* qs = sm;                                       // [HPC] all queries (scaled q^)
+    uint8_t* dos = qs + HPC * kv_bytes;                     // [HPC] all dO rows
+    uint8_t* ks = dos + HPC * kv_bytes;                     // [HPC] my QB keys (k^)
+    uint8_t* vs = ks + HPC * QB * 64;                       // [HPC] my QB values
+    float* sv = reinterpret_cast<float*>(vs + HPC * QB * 64);
+    float* lse2 = sv + 64;                                  // [HPC][n_pad]
+    float* dl = lse2 + HPC * p.n_pad;                       // [HPC][n_pad]
+    int* basei = reinterpret_cast<int*>(dl + HPC * p.n_pad);   // [n_pad]
     float* bias = reinterpret_cast<float*>(basei + p.n_pad);
     if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
     else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
@@ -436,32 +463,33 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     const bool has_bias = p.bias_table != nullptr;
     if (has_bias) {
         const int nb = (2 * p.H - 1) * nW;
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) bias[i] = p.bias_table[(long long)head * nb + i] * LOG2E;
-        for (int i = threadIdx.x; i < p.n_pad; i += blockDim.x) {
-            const int ii = min(i, p.n - 1);
-            basei[i] = (ii / p.W + p.H - 1) * nW + (ii % p.W + p.W - 1);
-        }
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) bias[i] = p.bias_table[(long long)head0 * nb + i] * LOG2E;
+        for (int i = threadIdx.x; i < p.n_pad; i += blockDim.x) basei[i] = bias_base(p, i);
     }
-    for (int i = threadIdx.x; i < p.n_pad; i += blockDim.x) {
+    for (int idx = threadIdx.x; idx < p.n_pad * HPC; idx += blockDim.x) {
+        const int i = idx / HPC, h_ = idx - i * HPC;
         if (i < p.n) {
             const long long r = seq_row(p, s, i);
-            lse2[i] = p.lse[r * p.heads + head] * LOG2E;
-            dl[i] = p.delta[r * p.heads + head];
-        } else { lse2[i] = INFINITY; dl[i] = 0.f; }
+            lse2[h_ * p.n_pad + i] = p.lse[r * p.heads + head0 + h_] * LOG2E;
+            dl[h_ * p.n_pad + i] = p.delta[r * p.heads + head0 + h_];
+        } else { lse2[h_ * p.n_pad + i] = INFINITY; dl[h_ * p.n_pad + i] = 0.f; }
     }
     __syncthreads();
-    load_tile<true>(qs, p.q, p.ldq, p, s, head, 0, p.n_pad, sv, p.scale * LOG2E);
-    load_tile<false>(dos, p.d_o, (long long)p.heads * DH, p, s, head, 0, p.n_pad, nullptr, 1.0f);
-    load_tile<true>(ks, p.k, p.ldkv, p, s, head, kblk * QB, QB, sv + 32, 1.0f);
-    load_tile<false>(vs, p.v, p.ldkv, p, s, head, kblk * QB, QB, nullptr, 1.0f);
+    load_tile<true>(qs, kv_bytes, p.q, p.ldq, p, s, head0, HPC, 0, p.n_pad, sv, p.scale * LOG2E);
+    load_tile<false>(dos, kv_bytes, p.d_o, (long long)p.heads * DH, p, s, head0, HPC, 0, p.n_pad, nullptr, 1.0f);
+    load_tile<true>(ks, QB * 64, p.k, p.ldkv, p, s, head0, HPC, kblk * QB, QB, sv + 32, 1.0f);
+    load_tile<false>(vs, QB * 64, p.v, p.ldkv, p, s, head0, HPC, kblk * QB, QB, nullptr, 1.0f);
     __syncthreads();
 
-    const int row_base = kblk * QB + warp * 16;
+    const int row_base = kblk * QB + wq * 16;
     if (row_base >= p.n) return;
-    const uint32_t ks_a = smem_u32(ks), vs_a = smem_u32(vs), qs_a = smem_u32(qs), dos_a = smem_u32(dos);
+    const uint32_t ks_a = smem_u32(ks + hl * QB * 64), vs_a = smem_u32(vs + hl * QB * 64);
+    const uint32_t qs_a = smem_u32(qs + hl * kv_bytes), dos_a = smem_u32(dos + hl * kv_bytes);
+    const float* lse2h = lse2 + hl * p.n_pad;
+    const float* dlh = dl + hl * p.n_pad;
     uint32_t ak[2][4], av[2][4];
-    load_a_frags(ak, ks_a, warp * 16, lane);
-    load_a_frags(av, vs_a, warp * 16, lane);
+    load_a_frags(ak, ks_a, wq * 16, lane);
+    load_a_frags(av, vs_a, wq * 16, lane);
     const int g = lane >> 2, t = lane & 3;
     const int j0 = row_base + g, j1 = j0 + 8;
     int tab0 = 0, tab1 = 0;
@@ -475,41 +503,41 @@ attn_bwd_dkv_kernel(const AttnParams p) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) { dk[a][b] = 0.f; dv[a][b] = 0.f; }
 
-    for (int qb = 0; qb < p.n_pad / KB; ++qb) {
-        float pt[8][4], ds[8][4];
+    for (int qblk = 0; qblk < p.n_pad / KBLK; ++qblk) {
+        float pt[KBLK / 8][4], ds[KBLK / 8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < KBLK / 8; ++nt) {
             // S^T tile: rows = my keys, cols = queries
             float st[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_rowsB(st, ak, qs_a, qb * KB + nt * 8, lane);
-            const int i = qb * KB + nt * 8 + 2 * t;
+            mma_rowsB(st, ak, qs_a, qblk * KBLK + nt * 8, lane);
+            const int i = qblk * KBLK + nt * 8 + 2 * t;
             if (has_bias) {
                 const int b0 = basei[i], b1 = basei[i + 1];
                 st[0] += bias[b0 - tab0]; st[1] += bias[b1 - tab0];
                 st[2] += bias[b0 - tab1]; st[3] += bias[b1 - tab1];
             }
-            const float l0 = lse2[i], l1 = lse2[i + 1];
+            const float l0 = lse2h[i], l1 = lse2h[i + 1];      // +inf for padded queries -> P = 0
             pt[nt][0] = exp2f(st[0] - l0); pt[nt][1] = exp2f(st[1] - l1);
             pt[nt][2] = exp2f(st[2] - l0); pt[nt][3] = exp2f(st[3] - l1);
             float dp[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_rowsB(dp, av, dos_a, qb * KB + nt * 8, lane);
-            const float dd0 = dl[i], dd1 = dl[i + 1];
+            mma_rowsB(dp, av, dos_a, qblk * KBLK + nt * 8, lane);
+            const float dd0 = dlh[i], dd1 = dlh[i + 1];
             ds[nt][0] = pt[nt][0] * (dp[0] - dd0); ds[nt][1] = pt[nt][1] * (dp[1] - dd1);
             ds[nt][2] = pt[nt][2] * (dp[2] - dd0); ds[nt][3] = pt[nt][3] * (dp[3] - dd1);
         }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < KBLK / 16; ++kk) {
             uint32_t a[4];
             a[0] = pack_bf16(pt[2 * kk][0], pt[2 * kk][1]);
             a[1] = pack_bf16(pt[2 * kk][2], pt[2 * kk][3]);
             a[2] = pack_bf16(pt[2 * kk + 1][0], pt[2 * kk + 1][1]);
             a[3] = pack_bf16(pt[2 * kk + 1][2], pt[2 * kk + 1][3]);
-            mma_colsB(dv, a, dos_a, qb * KB + kk * 16, lane);
+            mma_colsB(dv, a, dos_a, qblk * KBLK + kk * 16, lane);
             a[0] = pack_bf16(ds[2 * kk][0], ds[2 * kk][1]);
             a[1] = pack_bf16(ds[2 * kk][2], ds[2 * kk][3]);
             a[2] = pack_bf16(ds[2 * kk + 1][0], ds[2 * kk + 1][1]);
             a[3] = pack_bf16(ds[2 * kk + 1][2], ds[2 * kk + 1][3]);
-            mma_colsB(dk, a, qs_a, qb * KB + kk * 16, lane);
+            mma_colsB(dk, a, qs_a, qblk * KBLK + kk * 16, lane);
         }
     }
 #pragma unroll
@@ -533,23 +561,49 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     }
 }
 
-static int fill_params(AttnParams& p, int B, int T, int H, int W, int heads, int mode) {
+// ---------------------------------------------------------------------------------------------
+// host side: configuration selection and launches
+// ---------------------------------------------------------------------------------------------
+static int fill_params(AttnParams& p, int B, int T, int H, int W, int heads, int mode, int kblk) {
     CTC_REQUIRE(mode == CTC_MODE_SPATIAL || mode == CTC_MODE_TEMPORAL, "attention: bad mode %d", mode);
     p.heads = heads; p.mode = mode; p.T = T; p.HW = H * W; p.H = H; p.W = W;
     p.n = (mode == CTC_MODE_SPATIAL) ? H * W : T;
     p.n_seq = (mode == CTC_MODE_SPATIAL) ? B * T : B * H * W;
-    p.n_pad = (p.n + KB - 1) / KB * KB;
+    p.n_pad = (p.n + kblk - 1) / kblk * kblk;
     CTC_REQUIRE(p.n_pad <= 1024, "attention: sequence length %d exceeds the shared-memory resident design (1024)", p.n);
     return 0;
 }
 
 template <typename Kern>
-static int set_smem(Kern kern, size_t bytes, size_t& configured) {
-    if (bytes > configured) {
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = bytes;
+static int launch_attn(Kern kern, const AttnParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;   // one static per kernel instantiation
+    if (smem > configured) {
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
+    kern<<<grid, threads, smem, st>>>(p);
+    CTC_LAUNCH_CHECK();
     return 0;
+}
+
+// small-sequence configuration (temporal, n <= 32): all heads of a sequence in one CTA when heads % 8 == 0
+static bool use_small(const AttnParams& p) { return p.n <= 32 && p.bias_table == nullptr; }
+
+template <int QB, int KBLK, int HPC, bool PROBS>
+static int run_fwd(AttnParams& p, cudaStream_t st) {
+    const size_t nb = p.bias_table ? (size_t)(2 * p.H - 1) * (2 * p.W - 1) : 0;
+    const size_t smem = (size_t)HPC * (p.n_pad * 128 + QB * 64) + 256 + p.n_pad * 4 + nb * 4;
+    dim3 grid(p.n_seq, p.heads / HPC, (p.n + QB - 1) / QB);
+    return launch_attn(attn_fwd_kernel<QB, KBLK, HPC, PROBS>, p, grid, HPC * (QB / 16) * 32, smem, st);
+}
+template <int QB, int KBLK, int HPC>
+static int run_bwd(AttnParams& p, cudaStream_t st) {
+    const size_t nb = p.bias_table ? (size_t)(2 * p.H - 1) * (2 * p.W - 1) : 0;
+    dim3 grid(p.n_seq, p.heads / HPC, (p.n + QB - 1) / QB);
+    const size_t smem_dq = (size_t)HPC * (p.n_pad * 128 + 2 * QB * 64 + QB * 4) + 256 + p.n_pad * 4 + nb * 4;
+    if (int e = launch_attn(attn_bwd_dq_kernel<QB, KBLK, HPC>, p, grid, HPC * (QB / 16) * 32, smem_dq, st)) return e;
+    const size_t smem_dkv = (size_t)HPC * (p.n_pad * 128 + 2 * QB * 64 + 2 * p.n_pad * 4) + 256 + p.n_pad * 4 + nb * 4;
+    return launch_attn(attn_bwd_dkv_kernel<QB, KBLK, HPC>, p, grid, HPC * (QB / 16) * 32, smem_dkv, st);
 }
 
 }  // namespace ctc
@@ -560,36 +614,32 @@ extern "C" int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, cons
                                  int H, int W, int heads, const float* q_scale, const float* k_scale, float scale,
                                  const float* bias_table, int mode, void* o, float* lse, void* stream) {
     AttnParams p{};
-    if (int e = fill_params(p, B, T, H, W, heads, mode)) return e;
+    p.bias_table = bias_table;
+    const int n = (mode == CTC_MODE_SPATIAL) ? H * W : T;
+    const bool small = n <= 32 && bias_table == nullptr;
+    if (int e = fill_params(p, B, T, H, W, heads, mode, small ? 32 : 64)) return e;
     p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
-    p.ldkv = ldkv; p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale; p.bias_table = bias_table;
+    p.ldkv = ldkv; p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale;
     p.out = (__nv_bfloat16*)o; p.lse = lse;
-    const size_t nb = bias_table ? (size_t)(2 * H - 1) * (2 * W - 1) : 0;
-    const size_t smem = (size_t)p.n_pad * 128 + QB * 64 + 256 + p.n_pad * 4 + nb * 4;
-    static size_t configured = 0;
-    if (int e = set_smem(attn_fwd_kernel<false>, smem, configured)) return e;
-    dim3 grid(p.n_seq, heads, (p.n + QB - 1) / QB);
-    attn_fwd_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(p);
-    CTC_LAUNCH_CHECK();
-    return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (small) return (heads % 8 == 0) ? run_fwd<32, 32, 8, false>(p, st) : run_fwd<32, 32, 1, false>(p, st);
+    return (p.n > 128) ? run_fwd<192, 64, 1, false>(p, st) : run_fwd<64, 64, 1, false>(p, st);
 }
 
 extern "C" int ctc_attention_probs(const void* q, int64_t ldq, const void* k, int64_t ldkv, const float* lse, int B,
                                    int T, int H, int W, int heads, const float* q_scale, const float* k_scale,
                                    float scale, const float* bias_table, int mode, float* probs, void* stream) {
     AttnParams p{};
-    if (int e = fill_params(p, B, T, H, W, heads, mode)) return e;
+    p.bias_table = bias_table;
+    const int n = (mode == CTC_MODE_SPATIAL) ? H * W : T;
+    const bool small = n <= 32 && bias_table == nullptr;
+    if (int e = fill_params(p, B, T, H, W, heads, mode, small ? 32 : 64)) return e;
     p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.k = (const __nv_bfloat16*)k; p.v = nullptr; p.ldkv = ldkv;
-    p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale; p.bias_table = bias_table;
+    p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale;
     p.lse = const_cast<float*>(lse); p.probs = probs;
-    const size_t nb = bias_table ? (size_t)(2 * H - 1) * (2 * W - 1) : 0;
-    const size_t smem = (size_t)p.n_pad * 128 + QB * 64 + 256 + p.n_pad * 4 + nb * 4;
-    static size_t configured = 0;
-    if (int e = set_smem(attn_fwd_kernel<true>, smem, configured)) return e;
-    dim3 grid(p.n_seq, heads, (p.n + QB - 1) / QB);
-    attn_fwd_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(p);
-    CTC_LAUNCH_CHECK();
-    return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (small) return (heads % 8 == 0) ? run_fwd<32, 32, 8, true>(p, st) : run_fwd<32, 32, 1, true>(p, st);
+    return (p.n > 128) ? run_fwd<192, 64, 1, true>(p, st) : run_fwd<64, 64, 1, true>(p, st);
 }
 
 extern "C" int ctc_attention_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* o,
@@ -598,28 +648,16 @@ extern "C" int ctc_attention_bwd(const void* q, int64_t ldq, const void* k, cons
                                  int mode, void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* delta_ws,
                                  void* stream) {
     AttnParams p{};
-    if (int e = fill_params(p, B, T, H, W, heads, mode)) return e;
+    p.bias_table = bias_table;
+    const int n = (mode == CTC_MODE_SPATIAL) ? H * W : T;
+    const bool small = n <= 32 && bias_table == nullptr;
+    if (int e = fill_params(p, B, T, H, W, heads, mode, small ? 32 : 64)) return e;
     p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
     p.ldkv = ldkv; p.o = (const __nv_bfloat16*)o; p.d_o = (const __nv_bfloat16*)d_o;
-    p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale; p.bias_table = bias_table;
+    p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale;
     p.lse = const_cast<float*>(lse); p.delta = delta_ws;
     p.dq = (__nv_bfloat16*)dq; p.lddq = lddq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddkv = lddkv;
-    const size_t nb = bias_table ? (size_t)(2 * H - 1) * (2 * W - 1) : 0;
-    {
-        const size_t smem = (size_t)p.n_pad * 128 + 2 * QB * 64 + 256 + QB * 4 + p.n_pad * 4 + nb * 4;
-        static size_t configured = 0;
-        if (int e = set_smem(attn_bwd_dq_kernel, smem, configured)) return e;
-        dim3 grid(p.n_seq, heads, (p.n + QB - 1) / QB);
-        attn_bwd_dq_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
-        CTC_LAUNCH_CHECK();
-    }
-    {
-        const size_t smem = (size_t)p.n_pad * 128 + 2 * QB * 64 + 256 + 3 * p.n_pad * 4 + nb * 4;
-        static size_t configured = 0;
-        if (int e = set_smem(attn_bwd_dkv_kernel, smem, configured)) return e;
-        dim3 grid(p.n_seq, heads, (p.n + QB - 1) / QB);
-        attn_bwd_dkv_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
-        CTC_LAUNCH_CHECK();
-    }
-    return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (small) return (heads % 8 == 0) ? run_bwd<32, 32, 8>(p, st) : run_bwd<32, 32, 1>(p, st);
+    return (p.n > 128) ? run_bwd<96, 64, 1>(p, st) : run_bwd<64, 64, 1>(p, st);
 }

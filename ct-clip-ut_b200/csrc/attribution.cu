@@ -205,9 +205,144 @@ ig_combine_kernel(const float* __restrict__ vol, const float* __restrict__ gsum,
     if ((threadIdx.x & 31) == 0) { atomic_min_float(mm, mn); atomic_max_float(mm + 1, mx); }
 }
 
+// global min / max of an fp32 array of arbitrary sign (mm[0] = min, mm[1] = max; caller pre-sets +inf / -inf)
+CTC_DEVINL void atomic_min_any(float* addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+CTC_DEVINL void atomic_max_any(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__global__ void __launch_bounds__(256)
+minmax_kernel(const float* __restrict__ x, long long n, float* __restrict__ mm) {
+    float mn = 3.0e38f, mx = -3.0e38f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    mn = -warp_max(-mn);
+    if ((threadIdx.x & 31) == 0) { atomic_min_any(mm, mn); atomic_max_any(mm + 1, mx); }
+}
+
+// the reference's three normalisations + optional np.rot90(k=-1, axes=(1,2)):
+//   mode 0: (v-min)/(max+1e-8)   mode 1: (v-min)/(max-min+1e-8)   mode 2: v/(max+1e-8)
+// out[z, x, H-1-y] = f(in[z, y, x]) when rot (out shape [D, W, H]).
+__global__ void __launch_bounds__(256)
+normalize_kernel(const float* __restrict__ in, int D, int H, int W, const float* __restrict__ mm, int mode, int rot,
+                 float* __restrict__ out) {
+    const int OY = rot ? W : H, OX = rot ? H : W;
+    const long long total = (long long)D * OY * OX;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = (int)(idx % OX), oy = (int)((idx / OX) % OY), z = (int)(idx / ((long long)OX * OY));
+    const int y = rot ? (H - 1 - ox) : oy, x = rot ? oy : ox;
+    const float v = in[((long long)z * H + y) * W + x];
+    const float mn = mm[0], mx = mm[1];
+    float o;
+    if (mode == 0) o = (v - mn) / (mx + 1e-8f);
+    else if (mode == 1) o = (v - mn) / (mx - mn + 1e-8f);
+    else o = v / (mx + 1e-8f);
+    out[idx] = o;
+}
+
+// 16-bit radix histogram of the fp32 bit patterns (non-negative values: bit order == numeric order).
+// Counts (bits >> shift) & 0xffff of the elements whose bits above (shift+16) equal `prefix`.
+__global__ void __launch_bounds__(256)
+hist16_kernel(const float* __restrict__ x, long long n, int shift, unsigned int prefix, unsigned int* __restrict__ hist) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned int b = __float_as_uint(x[i]);
+        if (shift == 0 && (b >> 16) != prefix) continue;
+        atomicAdd(&hist[(b >> shift) & 0xffffu], 1u);
+    }
+}
+
+// integrated-gradients finalisation, second half (visualizations.py:882-901):
+//   n1 = (ig - min)/(max + 1e-8);  n2 = n1 >= q ? n1 : 0;  n3 = n2 ** 0.05;  out = n3 / (max(n3) + 1e-8);  rot90
+__global__ void __launch_bounds__(256)
+ig_finalize_kernel(const float* __restrict__ ig, int D, int H, int W, float mn, float mx, float q, float inv_m3, int rot,
+                   float* __restrict__ out) {
+    const int OY = rot ? W : H, OX = rot ? H : W;
+    const long long total = (long long)D * OY * OX;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = (int)(idx % OX), oy = (int)((idx / OX) % OY), z = (int)(idx / ((long long)OX * OY));
+    const int y = rot ? (H - 1 - ox) : oy, x = rot ? oy : ox;
+    const float n1 = (ig[((long long)z * H + y) * W + x] - mn) / (mx + 1e-8f);
+    const float n2 = (n1 >= q) ? n1 : 0.f;
+    out[idx] = (n2 > 0.f ? powf(n2, 0.05f) : 0.f) * inv_m3;
+}
+
+// occlusion heat map (visualizations.py:366-367, 390-392, 411-413): windows form a regular grid
+// (d0 = i*sd, ...), so voxel (z,y,x) is covered by at most ceil(p/s)^3 of them; sum their importances
+// in double (the reference accumulates float64 numpy arrays), divide by the count (0 -> 1).
+// imp fp32 [nd, nh, nw]; inc uint8 [nd, nh, nw] marks windows that were evaluated (sharding may drop some).
+__global__ void __launch_bounds__(256)
+occlusion_heat_kernel(const float* __restrict__ imp, const unsigned char* __restrict__ inc, int nd, int nh, int nw,
+                      int pd, int ph, int pw, int sd, int sh, int sw, int D, int H, int W, float* __restrict__ heat) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)D * H * W) return;
+    const int x = (int)(idx % W), y = (int)((idx / W) % H), z = (int)(idx / ((long long)W * H));
+    auto lo = [](int v, int p, int s) { const int t = v - p + 1; return t <= 0 ? 0 : (t + s - 1) / s; };
+    const int i0 = lo(z, pd, sd), i1 = min(z / sd, nd - 1);
+    const int j0 = lo(y, ph, sh), j1 = min(y / sh, nh - 1);
+    const int k0 = lo(x, pw, sw), k1 = min(x / sw, nw - 1);
+    double acc = 0.0;
+    int cnt = 0;
+    for (int i = i0; i <= i1; ++i)
+        for (int j = j0; j <= j1; ++j)
+            for (int k = k0; k <= k1; ++k) {
+                const int w = (i * nh + j) * nw + k;
+                if (inc[w]) { acc += (double)imp[w]; ++cnt; }
+            }
+    heat[idx] = (float)acc / (float)(cnt == 0 ? 1 : cnt);
+}
+
 }  // namespace ctc
 
 using namespace ctc;
+
+extern "C" int ctc_minmax(const float* x, int64_t n, float* mm, void* stream) {
+    minmax_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(x, n, mm);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_normalize(const float* in, int D, int H, int W, const float* mm, int mode, int rot90, float* out,
+                             void* stream) {
+    CTC_REQUIRE(in != out || !rot90, "normalize: rot90 cannot run in place");
+    const long long total = (long long)D * H * W;
+    normalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, D, H, W, mm, mode, rot90, out);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_hist16(const float* x, int64_t n, int shift, unsigned int prefix, unsigned int* hist, void* stream) {
+    CTC_REQUIRE(shift == 0 || shift == 16, "hist16: shift must be 0 or 16");
+    CTC_CHECK_CUDA(cudaMemsetAsync(hist, 0, 65536 * sizeof(unsigned int), (cudaStream_t)stream));
+    hist16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(x, n, shift, prefix, hist);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_ig_finalize(const float* ig, int D, int H, int W, float mn, float mx, float q, float inv_m3,
+                               int rot90, float* out, void* stream) {
+    const long long total = (long long)D * H * W;
+    ig_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ig, D, H, W, mn, mx, q, inv_m3,
+                                                                                         rot90, out);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_occlusion_heatmap(const float* imp, const unsigned char* inc, int nd, int nh, int nw, int pd, int ph,
+                                     int pw, int sd, int sh, int sw, int D, int H, int W, float* heat, void* stream) {
+    const long long total = (long long)D * H * W;
+    occlusion_heat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        imp, inc, nd, nh, nw, pd, ph, pw, sd, sh, sw, D, H, W, heat);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int ctc_rollout_spatial(const float* probs, int n_slices, int heads, int n, float* out, void* stream) {
     CTC_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)n_slices * n * sizeof(float), (cudaStream_t)stream));

@@ -31,7 +31,12 @@ void set_last_error(const char* fmt, ...);
             return 2;                                                                   \
         }                                                                               \
     } while (0)
-#define CTC_LAUNCH_CHECK() CTC_CHECK_CUDA(cudaGetLastError())
+void count_launch();
+#define CTC_LAUNCH_CHECK()                    \
+    do {                                      \
+        ::ctc::count_launch();                \
+        CTC_CHECK_CUDA(cudaGetLastError());   \
+    } while (0)
 
 // ----------------------------------------------------------------------------------------
 // small math / packing
@@ -102,6 +107,17 @@ CTC_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
             __trap();
         }
     }
+}
+
+// ----------------------------------------------------------------------------------------
+// cp.async (LDGSTS): 16-byte global -> shared copies that do not occupy registers, so one thread can
+// keep dozens of them in flight (memory-level parallelism for the HBM-bound tile loaders)
+// ----------------------------------------------------------------------------------------
+CTC_DEVINL void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+CTC_DEVINL void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // ----------------------------------------------------------------------------------------

@@ -103,53 +103,85 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// PEG: depthwise 3x3x3 stencil over the token grid, channels-last, 4 channels per thread.
+// PEG: depthwise 3x3x3 stencil over the token grid, channels-last.
 // Kernel tap (a, b, c) (the Conv3d kernel indices over the reinterpreted (t',h',w') axes, with
 // causal padding (2,0) on t' and (1,1) on h', w') maps to a canonical-grid offset:
 //   SPATIAL : (dt, dh, dw) = (a-2, b-1, c-1)
 //   TEMPORAL: (t',h',w') = (h, w, t)  =>  (dt, dh, dw) = (c-1, a-2, b-1)
-// The adjoint (transpose=1) gathers with the negated offsets.
+// The adjoint (sign = -1) gathers with the negated offsets.
+//
+// HBM-bound design (28 MB in / 28 MB out per volume): a naive 27-tap gather re-reads every input
+// 27x through L2 and is L2-bandwidth bound.  Here a thread owns ONE channel and walks along w with a
+// 9-row x 3-column register window (9 new 4-byte loads per output instead of 27; a warp's 32 lanes
+// are 32 consecutive channels = one 128-byte line per load), the 27 weights live in registers, and
+// the 16 warps of a CTA cover a 2 (t) x 8 (h) tile of the same channel chunk so that the remaining
+// 9x row reuse is served by L1.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static constexpr int PEG_TT = 2, PEG_TH = 8;
+
+__global__ void __launch_bounds__(PEG_TT * PEG_TH * 32)
 peg_kernel(const float* __restrict__ x, int B, int T, int H, int W, int C, const float* __restrict__ w27,
            const float* __restrict__ bias, int mode, int sign, float* __restrict__ y,
            __nv_bfloat16* __restrict__ y_bf16) {
-    const int c4 = C >> 2;
-    const long long total = (long long)B * T * H * W * c4;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % c4) * 4;
-    long long tok = idx / c4;
-    const int w = (int)(tok % W);
-    const int h = (int)((tok / W) % H);
-    const int t = (int)((tok / ((long long)W * H)) % T);
-    const long long base_b = (tok / ((long long)W * H * T)) * T * H * W;
-    const float4 self = *reinterpret_cast<const float4*>(x + tok * C + c);
-    float4 acc = self;
-    if (bias && sign > 0) {
-        const float4 b = *reinterpret_cast<const float4*>(bias + c);
-        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const int h = blockIdx.y * PEG_TH + (warp % PEG_TH);
+    const int tiles_t = (T + PEG_TT - 1) / PEG_TT;
+    const int t = (blockIdx.z % tiles_t) * PEG_TT + warp / PEG_TH;
+    const int b = blockIdx.z / tiles_t;
+    if (h >= H || t >= T || c >= C) return;
+    // weights: wk[k9][cw] for the 9 non-w taps x 3 w taps
+    float wk[9][3];
+    const float* rowp[9];
+#pragma unroll
+    for (int k9 = 0; k9 < 9; ++k9) {
+        const int p = k9 / 3, q = k9 % 3;
+        int dt, dh;
+        if (mode == CTC_MODE_SPATIAL) { dt = p - 2; dh = q - 1; } else { dh = p - 2; dt = q - 1; }
+#pragma unroll
+        for (int cw = 0; cw < 3; ++cw) {
+            const int tap = (mode == CTC_MODE_SPATIAL) ? (p * 3 + q) * 3 + cw : (p * 3 + cw) * 3 + q;
+            wk[k9][cw] = w27[tap * C + c];
+        }
+        const int tt = t + sign * dt, hh = h + sign * dh;
+        rowp[k9] = (tt >= 0 && tt < T && hh >= 0 && hh < H)
+                       ? x + ((((long long)b * T + tt) * H + hh) * W) * C + c : nullptr;
     }
+    const float bv = (bias && sign > 0) ? bias[c] : 0.f;
+    // register window: columns w-1, w, w+1, plus column w+2 already in flight (`pre`); the loads issued in
+    // iteration w (column w+3) are first consumed two iterations later, which hides the L2 latency
+    float win[9][3], pre[9];
+    const long long cs = C;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
+    for (int k9 = 0; k9 < 9; ++k9) {
+        win[k9][0] = 0.f;
+        win[k9][1] = rowp[k9] ? rowp[k9][0] : 0.f;
+        win[k9][2] = (rowp[k9] && W > 1) ? rowp[k9][cs] : 0.f;
+        pre[k9] = (rowp[k9] && W > 2) ? rowp[k9][2 * cs] : 0.f;
+    }
+    const long long out_base = ((((long long)b * T + t) * H + h) * W) * C + c;
+    for (int w = 0; w < W; ++w) {
+        float ld[9];
+        const bool more = (w + 3 < W);
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
+        for (int k9 = 0; k9 < 9; ++k9) ld[k9] = (more && rowp[k9]) ? rowp[k9][(long long)(w + 3) * cs] : 0.f;
+        float acc = win[7][1] + bv;   // k9 = 7 is the (dt, dh) = (0, 0) row: the residual term
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-                int dt, dh, dw;
-                if (mode == CTC_MODE_SPATIAL) { dt = a - 2; dh = b - 1; dw = cc - 1; }
-                else { dt = cc - 1; dh = a - 2; dw = b - 1; }
-                const int tt = t + sign * dt, hh = h + sign * dh, ww = w + sign * dw;
-                if (tt < 0 || tt >= T || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-                const float4 v = *reinterpret_cast<const float4*>(x + (base_b + ((long long)tt * H + hh) * W + ww) * C + c);
-                const float4 k = *reinterpret_cast<const float4*>(w27 + ((a * 3 + b) * 3 + cc) * C + c);
-                acc.x += v.x * k.x; acc.y += v.y * k.y; acc.z += v.z * k.z; acc.w += v.w * k.w;
-            }
+        for (int k9 = 0; k9 < 9; ++k9) {
+            // forward: tap cw reads x[w + cw - 1]; adjoint: x[w - (cw - 1)]
+            if (sign > 0) acc += wk[k9][0] * win[k9][0] + wk[k9][1] * win[k9][1] + wk[k9][2] * win[k9][2];
+            else          acc += wk[k9][2] * win[k9][0] + wk[k9][1] * win[k9][1] + wk[k9][0] * win[k9][2];
+        }
+        y[out_base + (long long)w * cs] = acc;
+        if (y_bf16) y_bf16[out_base + (long long)w * cs] = __float2bfloat16(acc);
+#pragma unroll
+        for (int k9 = 0; k9 < 9; ++k9) {
+            win[k9][0] = win[k9][1];
+            win[k9][1] = win[k9][2];
+            win[k9][2] = pre[k9];
+            pre[k9] = ld[k9];
         }
     }
-    *reinterpret_cast<float4*>(y + tok * C + c) = acc;
-    if (y_bf16)
-        *reinterpret_cast<uint2*>(y_bf16 + tok * C + c) = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -256,12 +288,13 @@ extern "C" int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, 
 
 extern "C" int ctc_peg(const float* x, int B, int T, int H, int W, int C, const float* w27, const float* bias,
                        int mode, int transpose, float* y, void* y_bf16, void* stream) {
-    CTC_REQUIRE(C % 4 == 0, "peg: C=%d must be a multiple of 4", C);
     CTC_REQUIRE(x != y, "peg: in-place stencil is not supported");
     CTC_REQUIRE(mode == CTC_MODE_SPATIAL || (T == H && H == W),
                 "peg: temporal mode reinterprets (h,w,t) as (t,h,w) and needs T==H==W (got %d,%d,%d)", T, H, W);
-    const long long total = (long long)B * T * H * W * (C / 4);
-    peg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    const int tiles_t = (T + PEG_TT - 1) / PEG_TT;
+    CTC_REQUIRE((long long)B * tiles_t <= 65535, "peg: batch %d too large for one launch", B);
+    dim3 grid((C + 31) / 32, (H + PEG_TH - 1) / PEG_TH, B * tiles_t);
+    peg_kernel<<<grid, PEG_TT * PEG_TH * 32, 0, (cudaStream_t)stream>>>(
         x, B, T, H, W, C, w27, bias, mode, transpose ? -1 : 1, y, (__nv_bfloat16*)y_bf16);
     CTC_LAUNCH_CHECK();
     return 0;

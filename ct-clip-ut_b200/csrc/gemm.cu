@@ -39,7 +39,9 @@ struct GemmSmem {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kStageOut = 4 * 4096;               // epilogue staging: 4 warps x (32 rows x 128 B)
+    static constexpr int kOutOffset = kStages * kStageBytes;
+    static constexpr int kBarOffset = kOutOffset + kStageOut;
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
@@ -101,6 +103,67 @@ CTC_DEVINL void epilogue_store(const GemmArgs& g, int row, int col0, const uint3
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// staged epilogue: the accumulator arrives one row per thread (TMEM lane), which would make every
+// global access a 32-row scatter.  Each epilogue warp therefore bounces its 32 x 128-byte chunk
+// through a private, XOR-swizzled (bank-conflict-free) shared-memory tile and then touches global
+// memory with one 16-byte access per lane such that a warp instruction covers 4 full 128-byte row
+// segments: residual / bias loads and the final stores are fully coalesced.
+// ---------------------------------------------------------------------------------------------
+CTC_DEVINL uint32_t stage_off(int row, int unit) { return (uint32_t)(row * 128 + ((unit ^ (row & 7)) << 4)); }
+
+// fp32 chunk: 32 rows x 32 columns
+CTC_DEVINL void epilogue_f32_staged(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
+                                    const uint32_t (&acc)[32], const float4 (&res)[8], bool has_res) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
+            make_uint4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+    __syncwarp();
+    const int u = lane & 7;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.bias) b = *reinterpret_cast<const float4*>(g.bias + col0 + u * 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = (lane >> 3) + 4 * i;
+        const int row = row0 + rl;
+        float4 v = *reinterpret_cast<const float4*>(stage + stage_off(rl, u));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+        if (row < g.M)
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (long long)row * g.ldc + col0 + u * 4) = v;
+    }
+    __syncwarp();
+}
+CTC_DEVINL void prefetch_resid(const GemmArgs& g, int row0, int col0, int lane, float4 (&res)[8]) {
+    const int u = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = row0 + (lane >> 3) + 4 * i;
+        res[i] = (row < g.M) ? *reinterpret_cast<const float4*>(g.resid + (long long)row * g.ldr + col0 + u * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+// bf16 chunk: 32 rows x 64 columns (acc already packed to 32 x bf16x2)
+CTC_DEVINL void epilogue_bf16_staged(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
+                                     const uint32_t (&pk)[32]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
+            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    __syncwarp();
+    const int u = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = (lane >> 3) + 4 * i;
+        const int row = row0 + rl;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(rl, u));
+        if (row < g.M)
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (long long)row * g.ldc + col0 + u * 8) = v;
+    }
+    __syncwarp();
 }
 
 // running top-2 (value, column) over a row, used by the VQ nearest-code search
@@ -207,26 +270,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tcgen05_fence_after();
             const int row = tm * BM + ew * 32 + lane;
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
-            Top2 t2; t2.init();
+            uint8_t* stage = smem + S::kOutOffset + ew * 4096;
+            const int row0 = tm * BM + ew * 32;
+            if constexpr (EPI == CTC_EPI_ARGMAX) {
+                // four independent trackers break the 256-long dependent compare chain
+                Top2 t2[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) t2[i].init();
+                const bool full = (tn + 1) * BN <= g.N;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + c, v);
-                tmem_ld_wait();
-                const int col0 = tn * BN + c;
-                if constexpr (EPI == CTC_EPI_ARGMAX) {
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c, v);
+                    tmem_ld_wait();
+                    const int col0 = tn * BN + c;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (col0 + j < g.N) t2.push(__uint_as_float(v[j]), col0 + j);
-                } else {
-                    if (col0 < g.N) epilogue_store<EPI>(g, row, col0, v);
+                        if (full || col0 + j < g.N) t2[j & 3].push(__uint_as_float(v[j]), col0 + j);
                 }
-            }
-            if constexpr (EPI == CTC_EPI_ARGMAX) {
+#pragma unroll
+                for (int i = 1; i < 4; ++i) { t2[0].push(t2[i].v0, t2[i].i0); t2[0].push(t2[i].v1, t2[i].i1); }
                 if (row < g.M) {
                     const long long o = ((long long)row * g.n_tiles_n + tn) * 2;
-                    g.top2_val[o] = t2.v0; g.top2_val[o + 1] = t2.v1;
-                    g.top2_idx[o] = t2.i0; g.top2_idx[o + 1] = t2.i1;
+                    g.top2_val[o] = t2[0].v0; g.top2_val[o + 1] = t2[0].v1;
+                    g.top2_idx[o] = t2[0].i0; g.top2_idx[o + 1] = t2[0].i1;
+                }
+            } else if constexpr (EPI == CTC_EPI_F32) {
+                const bool aligned = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0) &&
+                                     (!g.resid || ((g.ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(g.resid) & 15) == 0)) &&
+                                     (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    const int col0 = tn * BN + c;
+                    if (col0 >= g.N) break;
+                    const bool fast = aligned && (col0 + 32 <= g.N);
+                    float4 res[8];
+                    if (fast && g.resid) prefetch_resid(g, row0, col0, lane, res);
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c, v);
+                    tmem_ld_wait();
+                    if (fast) epilogue_f32_staged(g, stage, row0, col0, lane, v, res, g.resid != nullptr);
+                    else epilogue_store<EPI>(g, row, col0, v);
+                }
+            } else {
+                const bool aligned = (g.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 64) {
+                    const int col0 = tn * BN + c;
+                    if (col0 >= g.N) break;
+                    uint32_t v[32], pk[32];
+                    tmem_ld_32x32b_x32(taddr + c, v);
+                    tmem_ld_wait();
+                    if (aligned && col0 + 64 <= g.N) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            pk[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                        tmem_ld_32x32b_x32(taddr + c + 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            pk[16 + j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                        epilogue_bf16_staged(g, stage, row0, col0, lane, pk);
+                    } else {
+                        epilogue_store<EPI>(g, row, col0, v);
+                        if (col0 + 32 < g.N) {
+                            tmem_ld_32x32b_x32(taddr + c + 32, v);
+                            tmem_ld_wait();
+                            epilogue_store<EPI>(g, row, col0 + 32, v);
+                        }
+                    }
                 }
             }
             tcgen05_fence_before();

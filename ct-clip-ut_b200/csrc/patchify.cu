@@ -27,13 +27,60 @@ CTC_DEVINL float perturb(float v, int d, int y, int x, float alpha, bool has_alp
     return v;
 }
 
-// smem tile: [pt*p rows][G*p floats]; stats per patch
+// Shared-memory tile: [pt*p rows][G*p floats] (the CTA's G patches side by side along W).
+// All index arithmetic in the hot loops is incremental (no integer division per element).
+
+// per-patch mean / rstd with the two-pass formula; thread -> fixed tile column, strided rows
+CTC_DEVINL void patch_stats(const float* tile, const PatchGeom& g, int rows, int rowlen, float eps, float* s_acc,
+                            float* s_mean, float* s_rstd) {
+    const int rg = blockDim.x / rowlen;                  // row groups (rowlen <= blockDim.x by construction)
+    const int col = threadIdx.x % rowlen, r0 = threadIdx.x / rowlen;
+    const int j = col / g.p;
+    const bool active = r0 < rg;
+    if (threadIdx.x < 32) s_acc[threadIdx.x] = 0.f;
+    __syncthreads();
+    float s = 0.f;
+    if (active) for (int r = r0; r < rows; r += rg) s += tile[r * rowlen + col];
+    if (active) atomicAdd(&s_acc[j], s);
+    __syncthreads();
+    if (threadIdx.x < g.G) s_mean[threadIdx.x] = s_acc[threadIdx.x] / g.P;
+    __syncthreads();
+    if (threadIdx.x < 32) s_acc[threadIdx.x] = 0.f;
+    __syncthreads();
+    const float mean = s_mean[j];
+    float q = 0.f;
+    if (active) for (int r = r0; r < rows; r += rg) { const float d = tile[r * rowlen + col] - mean; q += d * d; }
+    if (active) atomicAdd(&s_acc[j], q);
+    __syncthreads();
+    if (threadIdx.x < g.G) s_rstd[threadIdx.x] = rsqrtf(s_acc[threadIdx.x] / g.P + eps);
+    __syncthreads();
+}
+
+// iterator over (patch j, tile row r, column c) for element pairs in patch-major order e = r*p + c
+struct PairIter {
+    int j, r, c, step_r, step_c, rows, p;
+    CTC_DEVINL void init(const PatchGeom& g, int rows_) {
+        rows = rows_; p = g.p;
+        const int e0 = 2 * threadIdx.x;                   // first pair of this thread (global pair index * 2)
+        j = e0 / g.P;
+        const int e = e0 % g.P;
+        r = e / p; c = e % p;
+        const int stride = 2 * blockDim.x;
+        step_r = stride / p; step_c = stride % p;
+    }
+    CTC_DEVINL void next() {
+        c += step_c; r += step_r;
+        if (c >= p) { c -= p; ++r; }
+        while (r >= rows) { r -= rows; ++j; }
+    }
+};
+
 __global__ void __launch_bounds__(256)
 patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, const float* __restrict__ alpha,
                        const int* __restrict__ occl, float oval, __nv_bfloat16* __restrict__ out) {
     extern __shared__ float tile[];
-    __shared__ float s_mean[32], s_rstd[32];
+    __shared__ float s_mean[32], s_rstd[32], s_acc[32];
     const int groups_w = g.Wp / g.G;
     int bid = blockIdx.x;
     const int gw = bid % groups_w; bid /= groups_w;
@@ -47,58 +94,65 @@ patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
     const float a = has_alpha ? alpha[b] : 1.f;
     const int* oc = occl ? occl + b * 6 : nullptr;
     const int x0 = gw * rowlen;
-    // ---- load (coalesced along W), apply perturbations
+    // ---- load: every thread issues all of its 16-byte async copies back to back (coalesced along W)
     const int vec_per_row = rowlen >> 2;
-    for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
-        const int r = i / vec_per_row, v4 = (i % vec_per_row) * 4;
-        const int d = tp * g.pt + r / g.p, y = hp * g.p + r % g.p;
-        float4 v = *reinterpret_cast<const float4*>(vb + ((long long)d * g.H + y) * g.W + x0 + v4);
-        v.x = perturb(v.x, d, y, x0 + v4 + 0, a, has_alpha, oc, oval);
-        v.y = perturb(v.y, d, y, x0 + v4 + 1, a, has_alpha, oc, oval);
-        v.z = perturb(v.z, d, y, x0 + v4 + 2, a, has_alpha, oc, oval);
-        v.w = perturb(v.w, d, y, x0 + v4 + 3, a, has_alpha, oc, oval);
-        *reinterpret_cast<float4*>(tile + r * rowlen + v4) = v;
-    }
-    __syncthreads();
-    // ---- per-patch statistics: warps loop over patches
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int j = warp; j < g.G; j += nwarps) {
-        float s = 0.f;
-        for (int e = lane; e < g.P; e += 32) s += tile[(e / g.p) * rowlen + j * g.p + e % g.p];
-        const float mean = warp_sum(s) / g.P;
-        float q = 0.f;
-        for (int e = lane; e < g.P; e += 32) {
-            const float dlt = tile[(e / g.p) * rowlen + j * g.p + e % g.p] - mean;
-            q += dlt * dlt;
+    {
+        int r = threadIdx.x / vec_per_row, v = threadIdx.x % vec_per_row;
+        const int dr = blockDim.x / vec_per_row, dv = blockDim.x % vec_per_row;
+        while (r < rows) {
+            const int pt_i = r / g.p;
+            const int d = tp * g.pt + pt_i, y = hp * g.p + (r - pt_i * g.p);
+            cp_async_16(tile + r * rowlen + v * 4, vb + ((long long)d * g.H + y) * g.W + x0 + v * 4);
+            v += dv; r += dr;
+            if (v >= vec_per_row) { v -= vec_per_row; ++r; }
         }
-        const float rstd = rsqrtf(warp_sum(q) / g.P + eps);
-        if (lane == 0) { s_mean[j] = mean; s_rstd[j] = rstd; }
     }
+    cp_async_wait_all();
     __syncthreads();
-    // ---- normalise + affine, write bf16 rows (2 elements per thread, contiguous along the patch row)
+    // ---- perturbations applied in shared memory (only when requested / when the cube touches this tile)
+    bool hit = false;
+    if (oc && oc[3] > 0) {
+        const int d0 = tp * g.pt, y0 = hp * g.p;
+        hit = d0 < oc[0] + oc[3] && d0 + g.pt > oc[0] && y0 < oc[1] + oc[4] && y0 + g.p > oc[1] &&
+              x0 < oc[2] + oc[5] && x0 + rowlen > oc[2];
+    }
+    if (has_alpha || hit) {
+        int r = threadIdx.x / rowlen, c = threadIdx.x % rowlen;
+        const int dr = blockDim.x / rowlen, dc = blockDim.x % rowlen;
+        while (r < rows) {
+            const int pt_i = r / g.p;
+            const int d = tp * g.pt + pt_i, y = hp * g.p + (r - pt_i * g.p);
+            tile[r * rowlen + c] = perturb(tile[r * rowlen + c], d, y, x0 + c, a, has_alpha, oc, oval);
+            c += dc; r += dr;
+            if (c >= rowlen) { c -= rowlen; ++r; }
+        }
+        __syncthreads();
+    }
+    patch_stats(tile, g, rows, rowlen, eps, s_acc, s_mean, s_rstd);
+    // ---- normalise + affine, write bf16 rows; consecutive threads write consecutive pairs of a patch row
     const long long tok0 = (((long long)b * g.T + tp) * g.Hp + hp) * g.Wp + (long long)gw * g.G;
-    const int half = g.P >> 1;
-    for (int i = threadIdx.x; i < g.G * half; i += blockDim.x) {
-        const int j = i / half, e = (i % half) * 2;
-        const float mean = s_mean[j], rstd = s_rstd[j];
-        const int r = e / g.p, c = e % g.p;  // p is even, so e and e+1 share a tile row
-        const float v0 = tile[r * rowlen + j * g.p + c], v1 = tile[r * rowlen + j * g.p + c + 1];
-        const float o0 = (v0 - mean) * rstd * gamma[e] + beta[e];
-        const float o1 = (v1 - mean) * rstd * gamma[e + 1] + beta[e + 1];
-        *reinterpret_cast<uint32_t*>(out + (tok0 + j) * g.P + e) = pack_bf16(o0, o1);
+    PairIter it; it.init(g, rows);
+    while (it.j < g.G) {
+        const int e = it.r * g.p + it.c;
+        const float mean = s_mean[it.j], rstd = s_rstd[it.j];
+        const float2 v = *reinterpret_cast<const float2*>(tile + it.r * rowlen + it.j * g.p + it.c);
+        const float2 gm = *reinterpret_cast<const float2*>(gamma + e);
+        const float2 bt = *reinterpret_cast<const float2*>(beta + e);
+        *reinterpret_cast<uint32_t*>(out + (tok0 + it.j) * g.P + e) =
+            pack_bf16((v.x - mean) * rstd * gm.x + bt.x, (v.y - mean) * rstd * gm.y + bt.y);
+        it.next();
     }
 }
 
 // Backward: dx' = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dY * gamma;  chain through
 // x' = 1 + alpha (x - 1) is NOT applied: IG differentiates w.r.t. the interpolated input itself
-// (visualizations.py:863,872).  Occluded voxels receive whatever gradient flows to x' (the
-// occlusion path is forward only, so the two are never combined).
+// (visualizations.py:863,872).  The occlusion path is forward only.
 __global__ void __launch_bounds__(256)
 patchify_ln_bwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* __restrict__ gamma, float eps,
                        const float* __restrict__ alpha, const __nv_bfloat16* __restrict__ dy,
                        float* __restrict__ grad, int sum_over_batch, float wscale) {
     extern __shared__ float tile[];
-    __shared__ float s_mean[32], s_rstd[32], s_mg[32], s_mgx[32];
+    __shared__ float s_mean[32], s_rstd[32], s_acc[32], s_mg[32], s_mgx[32];
     const int groups_w = g.Wp / g.G;
     int bid = blockIdx.x;
     const int gw = bid % groups_w; bid /= groups_w;
@@ -112,66 +166,94 @@ patchify_ln_bwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
     const float a = has_alpha ? alpha[b] : 1.f;
     const int x0 = gw * rowlen;
     const int vec_per_row = rowlen >> 2;
-    for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
-        const int r = i / vec_per_row, v4 = (i % vec_per_row) * 4;
-        const int d = tp * g.pt + r / g.p, y = hp * g.p + r % g.p;
-        float4 v = *reinterpret_cast<const float4*>(vb + ((long long)d * g.H + y) * g.W + x0 + v4);
-        if (has_alpha) {
-            v.x = 1.f + a * (v.x - 1.f); v.y = 1.f + a * (v.y - 1.f);
-            v.z = 1.f + a * (v.z - 1.f); v.w = 1.f + a * (v.w - 1.f);
-        }
-        *reinterpret_cast<float4*>(tile + r * rowlen + v4) = v;
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const long long tok0 = (((long long)b * g.T + tp) * g.Hp + hp) * g.Wp + (long long)gw * g.G;
-    for (int j = warp; j < g.G; j += nwarps) {
-        float s = 0.f;
-        for (int e = lane; e < g.P; e += 32) s += tile[(e / g.p) * rowlen + j * g.p + e % g.p];
-        const float mean = warp_sum(s) / g.P;
-        float q = 0.f;
-        for (int e = lane; e < g.P; e += 32) {
-            const float dlt = tile[(e / g.p) * rowlen + j * g.p + e % g.p] - mean;
-            q += dlt * dlt;
+    __nv_bfloat16* dys = reinterpret_cast<__nv_bfloat16*>(tile + rows * rowlen);   // [G][P] bf16 (contiguous in global)
+    {
+        int r = threadIdx.x / vec_per_row, v = threadIdx.x % vec_per_row;
+        const int dr = blockDim.x / vec_per_row, dv = blockDim.x % vec_per_row;
+        while (r < rows) {
+            const int pt_i = r / g.p;
+            const int d = tp * g.pt + pt_i, y = hp * g.p + (r - pt_i * g.p);
+            cp_async_16(tile + r * rowlen + v * 4, vb + ((long long)d * g.H + y) * g.W + x0 + v * 4);
+            v += dv; r += dr;
+            if (v >= vec_per_row) { v -= vec_per_row; ++r; }
         }
-        const float rstd = rsqrtf(warp_sum(q) / g.P + eps);
-        const __nv_bfloat16* dyr = dy + (tok0 + j) * g.P;
+        const int n16 = g.G * g.P / 8;                      // the CTA's G patches are adjacent rows of dY
+        const __nv_bfloat16* src = dy + tok0 * g.P;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async_16(dys + i * 8, src + i * 8);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (has_alpha) {
+        for (int i = threadIdx.x; i < rows * rowlen; i += blockDim.x) tile[i] = 1.f + a * (tile[i] - 1.f);
+        __syncthreads();
+    }
+    patch_stats(tile, g, rows, rowlen, eps, s_acc, s_mean, s_rstd);
+    // ---- per-patch mean(g) and mean(g * xhat): patch-major walk (coalesced dY reads), flush on patch change
+    if (threadIdx.x < 32) { s_mg[threadIdx.x] = 0.f; s_mgx[threadIdx.x] = 0.f; }
+    __syncthreads();
+    {
+        PairIter it; it.init(g, rows);
         float sg = 0.f, sgx = 0.f;
-        for (int e = lane; e < g.P; e += 32) {
-            const float gg = __bfloat162float(dyr[e]) * gamma[e];
-            const float xh = (tile[(e / g.p) * rowlen + j * g.p + e % g.p] - mean) * rstd;
-            sg += gg; sgx += gg * xh;
+        int cur = it.j;
+        while (it.j < g.G) {
+            if (it.j != cur) { atomicAdd(&s_mg[cur], sg); atomicAdd(&s_mgx[cur], sgx); sg = sgx = 0.f; cur = it.j; }
+            const int e = it.r * g.p + it.c;
+            const float mean = s_mean[it.j], rstd = s_rstd[it.j];
+            const float2 v = *reinterpret_cast<const float2*>(tile + it.r * rowlen + it.j * g.p + it.c);
+            const float2 gm = *reinterpret_cast<const float2*>(gamma + e);
+            const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dys + it.j * g.P + e));
+            const float g0 = d.x * gm.x, g1 = d.y * gm.y;
+            sg += g0 + g1;
+            sgx += g0 * (v.x - mean) * rstd + g1 * (v.y - mean) * rstd;
+            it.next();
         }
-        sg = warp_sum(sg) / g.P; sgx = warp_sum(sgx) / g.P;
-        if (lane == 0) { s_mean[j] = mean; s_rstd[j] = rstd; s_mg[j] = sg; s_mgx[j] = sgx; }
+        if (cur < g.G) { atomicAdd(&s_mg[cur], sg); atomicAdd(&s_mgx[cur], sgx); }
     }
     __syncthreads();
-    // overwrite the tile with dx (same element order), then store coalesced along W
-    for (int i = threadIdx.x; i < g.G * g.P; i += blockDim.x) {
-        const int j = i / g.P, e = i % g.P;
-        const int r = e / g.p, c = e % g.p;
-        const float mean = s_mean[j], rstd = s_rstd[j];
-        const float xh = (tile[r * rowlen + j * g.p + c] - mean) * rstd;
-        const float gg = __bfloat162float(dy[(tok0 + j) * g.P + e]) * gamma[e];
-        tile[r * rowlen + j * g.p + c] = rstd * (gg - s_mg[j] - xh * s_mgx[j]);
+    // ---- dx in place of x (same tile positions), then store coalesced along W
+    {
+        PairIter it; it.init(g, rows);
+        const float invP = 1.f / g.P;
+        while (it.j < g.G) {
+            const int e = it.r * g.p + it.c;
+            const float mean = s_mean[it.j], rstd = s_rstd[it.j];
+            const float mg = s_mg[it.j] * invP, mgx = s_mgx[it.j] * invP;
+            float2* tp2 = reinterpret_cast<float2*>(tile + it.r * rowlen + it.j * g.p + it.c);
+            const float2 v = *tp2;
+            const float2 gm = *reinterpret_cast<const float2*>(gamma + e);
+            const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dys + it.j * g.P + e));
+            float2 o;
+            o.x = rstd * (d.x * gm.x - mg - (v.x - mean) * rstd * mgx);
+            o.y = rstd * (d.y * gm.y - mg - (v.y - mean) * rstd * mgx);
+            *tp2 = o;
+            it.next();
+        }
     }
     __syncthreads();
     float* gb = grad + (sum_over_batch ? 0 : (long long)b * g.D * g.H * g.W);
-    for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
-        const int r = i / vec_per_row, v4 = (i % vec_per_row) * 4;
-        const int d = tp * g.pt + r / g.p, y = hp * g.p + r % g.p;
-        float4 v = *reinterpret_cast<const float4*>(tile + r * rowlen + v4);
-        float* dst = gb + ((long long)d * g.H + y) * g.W + x0 + v4;
-        if (sum_over_batch) {
-            atomicAdd(dst + 0, v.x * wscale); atomicAdd(dst + 1, v.y * wscale);
-            atomicAdd(dst + 2, v.z * wscale); atomicAdd(dst + 3, v.w * wscale);
-        } else {
-            *reinterpret_cast<float4*>(dst) = v;
+    {
+        int r = threadIdx.x / vec_per_row, v = threadIdx.x % vec_per_row;
+        const int dr = blockDim.x / vec_per_row, dv = blockDim.x % vec_per_row;
+        while (r < rows) {
+            const int v4 = v * 4;
+            const int pt_i = r / g.p;
+            const int d = tp * g.pt + pt_i, y = hp * g.p + (r - pt_i * g.p);
+            const float4 val = *reinterpret_cast<const float4*>(tile + r * rowlen + v4);
+            float* dst = gb + ((long long)d * g.H + y) * g.W + x0 + v4;
+            if (sum_over_batch) {
+                atomicAdd(dst + 0, val.x * wscale); atomicAdd(dst + 1, val.y * wscale);
+                atomicAdd(dst + 2, val.z * wscale); atomicAdd(dst + 3, val.w * wscale);
+            } else {
+                *reinterpret_cast<float4*>(dst) = val;
+            }
+            v += dv; r += dr;
+            if (v >= vec_per_row) { v -= vec_per_row; ++r; }
         }
     }
 }
 
-static int make_geom(PatchGeom& g, long long vol_stride, int B, int D, int H, int W, int pt, int p) {
+static int make_geom(PatchGeom& g, long long vol_stride, int B, int D, int H, int W, int pt, int p, int bytes_per_elem) {
     CTC_REQUIRE(D % pt == 0 && H % p == 0 && W % p == 0, "patchify: volume %dx%dx%d not divisible by patch %dx%dx%d",
                 D, H, W, pt, p, p);
     CTC_REQUIRE(p % 4 == 0, "patchify: patch size %d must be a multiple of 4 (128-bit loads)", p);
@@ -180,9 +262,10 @@ static int make_geom(PatchGeom& g, long long vol_stride, int B, int D, int H, in
     // patches per CTA: largest divisor of Wp with tile <= 96 KB and <= 32 patches
     int G = 1;
     for (int c = 1; c <= g.Wp && c <= 32; ++c)
-        if (g.Wp % c == 0 && (long long)c * g.P * 4 <= 96 * 1024) G = c;
+        if (g.Wp % c == 0 && (long long)c * g.P * bytes_per_elem <= 100 * 1024 && c * p <= 256) G = c;
     g.G = G;
-    CTC_REQUIRE((long long)G * g.P * 4 <= 200 * 1024, "patchify: patch of %d voxels does not fit shared memory", g.P);
+    CTC_REQUIRE((long long)G * g.P * bytes_per_elem <= 200 * 1024, "patchify: patch of %d voxels does not fit shared memory", g.P);
+    CTC_REQUIRE(g.P % 8 == 0, "patchify: patch volume %d must be a multiple of 8", g.P);
     return 0;
 }
 
@@ -194,7 +277,7 @@ extern "C" int ctc_patchify_ln_fwd(const float* volume, int64_t vol_batch_stride
                                    int p, const float* gamma, const float* beta, float eps, const float* alpha,
                                    const int* occl, float occl_value, void* out_bf16, void* stream) {
     PatchGeom g;
-    if (int e = make_geom(g, vol_batch_stride, B, D, H, W, pt, p)) return e;
+    if (int e = make_geom(g, vol_batch_stride, B, D, H, W, pt, p, 4)) return e;
     const size_t smem = (size_t)g.G * g.P * 4;
     static size_t configured = 0;
     if (smem > configured) {
@@ -212,8 +295,8 @@ extern "C" int ctc_patchify_ln_bwd(const float* volume, int64_t vol_batch_stride
                                    int p, const float* gamma, float eps, const float* alpha, const void* dy_bf16,
                                    float* grad, int sum_over_batch, float wscale, void* stream) {
     PatchGeom g;
-    if (int e = make_geom(g, vol_batch_stride, B, D, H, W, pt, p)) return e;
-    const size_t smem = (size_t)g.G * g.P * 4;
+    if (int e = make_geom(g, vol_batch_stride, B, D, H, W, pt, p, 6)) return e;
+    const size_t smem = (size_t)g.G * g.P * 6;
     static size_t configured = 0;
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -279,9 +279,49 @@ __global__ void latent_sim_kernel(const float* __restrict__ latent, const float*
     }
 }
 
+// dlatent_i = sum_j g_ij * temp * (t_j - un_i * cos_ij) / |u_i|
+__global__ void latent_sim_bwd_kernel(const float* __restrict__ latent, const float* __restrict__ text,
+                                      const float* __restrict__ gsim, int Bt, int NL, float temp,
+                                      float* __restrict__ dlatent) {
+    extern __shared__ float sm[];   // [Bt] cosines
+    __shared__ float s_inv;
+    const int i = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* u = latent + (long long)i * NL;
+    if (warp == 0) {
+        float ss = 0.f;
+        for (int n = lane; n < NL; n += 32) ss += u[n] * u[n];
+        ss = warp_sum(ss);
+        if (lane == 0) s_inv = 1.f / sqrtf(ss);
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    for (int j = warp; j < Bt; j += blockDim.x >> 5) {
+        float d = 0.f;
+        for (int n = lane; n < NL; n += 32) d += u[n] * inv * text[(long long)j * NL + n];
+        d = warp_sum(d);
+        if (lane == 0) sm[j] = d;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < NL; n += blockDim.x) {
+        const float un = u[n] * inv;
+        float acc = 0.f;
+        for (int j = 0; j < Bt; ++j) acc += gsim[(long long)i * Bt + j] * (text[(long long)j * NL + n] - un * sm[j]);
+        dlatent[(long long)i * NL + n] = acc * temp * inv;
+    }
+}
+
 }  // namespace ctc
 
 using namespace ctc;
+
+extern "C" int ctc_latent_sim_bwd(const float* latent, const float* text_latents, const float* gsim, int B, int Bt,
+                                  int NL, float temp, float* dlatent, void* stream) {
+    latent_sim_bwd_kernel<<<B, 128, Bt * sizeof(float), (cudaStream_t)stream>>>(latent, text_latents, gsim, Bt, NL,
+                                                                                temp, dlatent);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int ctc_vq_argmax(const float* x, const void* x_bf16, int R, int C, const float* codebook,
                              const void* codebook_bf16, int K, float* cand_val, int* cand_idx, int* ind,

@@ -40,6 +40,7 @@ SIGNATURES = {
     "ctc_latent_proj_bwd": [P, P, I, L, I, P, P],
     "ctc_text_latent": [P, P, I, I, I, P, P],
     "ctc_latent_sim": [P, P, I, I, I, F, P, P, P, P],
+    "ctc_latent_sim_bwd": [P, P, P, I, I, I, F, P, P],
     "ctc_rollout_spatial": [P, I, I, I, P, P],
     "ctc_rollout_temporal": [P, I, I, I, I, P, P],
     "ctc_attn_colmean": [P, I, I, I, P, P],
@@ -47,15 +48,20 @@ SIGNATURES = {
     "ctc_gradcam": [P, P, P, I, I, P, P],
     "ctc_upsample_trilinear": [P, I, I, I, P, I, I, I, I, P],
     "ctc_ig_combine": [P, P, L, F, P, P, P],
+    "ctc_minmax": [P, L, P, P],
+    "ctc_normalize": [P, I, I, I, P, I, I, P, P],
+    "ctc_hist16": [P, L, I, ctypes.c_uint, P, P],
+    "ctc_ig_finalize": [P, I, I, I, F, F, F, F, I, P, P],
+    "ctc_occlusion_heatmap": [P, P, I, I, I, I, I, I, I, I, I, I, I, I, P, P],
 }
-OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, [])}
+OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, []),
+                 "ctc_launch_count": (ctypes.c_longlong, [])}
 
 EPI_BF16, EPI_F32, EPI_ARGMAX = 0, 1, 2
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
 MODE_SPATIAL, MODE_TEMPORAL = 0, 1
 
 _lib = None
-_launches = 0
 
 
 def load() -> ctypes.CDLL:
@@ -101,14 +107,12 @@ def stream_ptr():
 
 def call(name: str, *args) -> None:
     """Invoke one C-ABI entry point; raises RuntimeError with ctc_last_error() on failure."""
-    global _launches
     lib = load()
     rc = getattr(lib, name)(*[ptr(a) for a in args])
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.ctc_last_error().decode(errors='replace')}")
-    _launches += 1
 
 
 def launch_count() -> int:
-    """Number of C-ABI calls issued so far (each launches >= 1 kernel); used by bench.py."""
-    return _launches
+    """Number of kernels the library has launched in this process (bench.py's gpu_launches)."""
+    return int(load().ctc_launch_count())

@@ -56,6 +56,7 @@ class Ctx:
     image_latents: torch.Tensor = None
     sim: torch.Tensor = None                   # fp32 [B, Bt]
     dlatent: torch.Tensor = None
+    text_latents: torch.Tensor = None
     tokens: Optional[torch.Tensor] = None      # fp32 [R, C] quantised tokens (optional)
     # gradient captures for Grad-CAM (visualizations.py:140-218): grads of the residual stream
     grads: Dict[str, torch.Tensor] = field(default_factory=dict)
@@ -131,7 +132,7 @@ class Engine:
         return x3, lc
 
     # ------------------------------------------------------------------ forward
-    def forward(self, volume: torch.Tensor, text_latents: torch.Tensor, batch: Optional[int] = None,
+    def forward(self, volume: torch.Tensor, text_latents: Optional[torch.Tensor], batch: Optional[int] = None,
                 alpha: Optional[torch.Tensor] = None, occl: Optional[torch.Tensor] = None,
                 occl_value: float = -1.0, save: bool = False, want_tokens: bool = False,
                 keep_attn: bool = False) -> Ctx:
@@ -194,6 +195,8 @@ class Engine:
         tokens = self._empty(R, C) if want_tokens else None
         call("ctc_vq_gather_pool", ind, pl.codebook, B, T, HW, C, pooled, None, tokens, stream_ptr())
         ctx.pooled, ctx.tokens = pooled, tokens
+        if text_latents is None:      # CTViT.forward alone (ctvit.py:105-125): stop after the VQ
+            return ctx
         L, NL = HW * C, cfg.dim_latent
         n_chunks = (L + 1023) // 1024
         partial = self._empty(n_chunks, B, NL)
@@ -204,6 +207,7 @@ class Engine:
         dlat = self._empty(B, NL) if save else None
         call("ctc_latent_sim", latent, text_latents, B, Bt, NL, pl.temp_exp, sim, il, dlat, stream_ptr())
         ctx.latent, ctx.image_latents, ctx.sim, ctx.dlatent = latent, il, sim, dlat
+        ctx.text_latents = text_latents
         return ctx
 
     # ------------------------------------------------------------------ backward
@@ -246,9 +250,11 @@ class Engine:
         return dx0, dx0_bf
 
     def backward(self, ctx: Ctx, grad_out: Optional[torch.Tensor] = None, sum_over_batch: bool = False,
-                 capture_grads: bool = False, to_input: bool = True) -> Optional[torch.Tensor]:
+                 capture_grads: bool = False, to_input: bool = True, gsim: Optional[torch.Tensor] = None
+                 ) -> Optional[torch.Tensor]:
         """Input gradient of sum_b sim[b, b % Bt] (the `sim[rank, rank].backward()` of
-        visualizations.py:580,786,868,921) w.r.t. the (interpolated) voxels.
+        visualizations.py:580,786,868,921) w.r.t. the (interpolated) voxels; with `gsim` fp32 [B, Bt]
+        the gradient of sum_ij gsim[i,j] * sim[i,j] instead.
         sum_over_batch: accumulate all batch rows into `grad_out` [D,H,W] (IG partial sum, +=).
         capture_grads: keep the residual-stream gradients Grad-CAM reads."""
         cfg, pl = self.cfg, self.plan
@@ -260,6 +266,12 @@ class Engine:
         cap = ctx.grads if capture_grads else None
         L, NL = HW * C, cfg.dim_latent
         dpooled = self._empty(B, L)
+        if gsim is not None:
+            Bt = ctx.text_latents.shape[0]
+            g = gsim.to(self.dev, torch.float32).contiguous()
+            assert g.shape == (B, Bt)
+            call("ctc_latent_sim_bwd", ctx.latent, ctx.text_latents, g, B, Bt, NL, pl.temp_exp, ctx.dlatent,
+                 stream_ptr())
         call("ctc_latent_proj_bwd", ctx.dlatent, pl.wv_bf16, B, L, NL, dpooled, stream_ptr())
         dxt = self._empty(R, C)
         call("ctc_vq_bwd", dpooled, None, ctx.x_pre_vq, B, T, HW, C, 0 if cfg.vq_grad_mode == "ste_l2norm" else 1,

@@ -39,6 +39,8 @@ int ctc_version(void);
 const char* ctc_last_error(void);
 /* 0 if the current device is compute capability 10.x; error otherwise (no fallback). */
 int ctc_device_check(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long ctc_launch_count(void);
 
 /* C[M,N] = A[M,K] * B[N,K]^T, bf16 operands (row strides lda/ldb elements), fp32 accumulate.
  * epi BF16: out bf16 [M,ldc]; F32: out fp32 = acc (+bias[N]) (+resid fp32 [M,ldr], may alias out).
@@ -134,6 +136,10 @@ int ctc_text_latent(const float* e, const float* wt, int Bt, int DT, int NL, flo
 int ctc_latent_sim(const float* latent, const float* text_latents, int B, int Bt, int NL, float temp, float* sim,
                    float* image_latents, float* dlatent, void* stream);
 
+/* General adjoint of ctc_latent_sim: dlatent[i,:] = sum_j gsim[i,j] * d sim[i,j] / d latent_i (gsim fp32 [B,Bt]). */
+int ctc_latent_sim_bwd(const float* latent, const float* text_latents, const float* gsim, int B, int Bt, int NL,
+                       float temp, float* dlatent, void* stream);
+
 /* Attention-rollout reductions (visualizations.py:707-743 as used at :800-841).
  * spatial: probs fp32 [n_slices, heads, n, n] -> out[n_slices, n] = colsum(rownorm(rownorm(mean_h P)+I)).
  * temporal: probs of all L layers, each [n_tok, heads, T, T] (layer stride = n_tok*heads*T*T) -> out[n_tok, T]. */
@@ -155,6 +161,25 @@ int ctc_upsample_trilinear(const float* in, int d, int h, int w, float* out, int
  * ig = relu((x - 1) * gsum * inv_steps), plus global min/max into mm[2] (mm pre-set to {+inf,-inf}). */
 int ctc_ig_combine(const float* volume, const float* gsum, int64_t n, float inv_steps, float* ig, float* mm,
                    void* stream);
+
+/* Global min/max of an fp32 array into mm[2] (caller pre-sets {+inf, -inf}). */
+int ctc_minmax(const float* x, int64_t n, float* mm, void* stream);
+/* The reference's normalisations: mode 0 (v-min)/(max+1e-8) [raw attention :674, Grad-CAM :946,
+ * IG :882]; mode 1 (v-min)/(max-min+1e-8) [rollout :812, occlusion :414]; mode 2 v/(max+1e-8) [IG :893];
+ * optional fused np.rot90(k=-1, axes=(1,2)): in [D,H,W] -> out [D,W,H]. */
+int ctc_normalize(const float* in, int D, int H, int W, const float* mm, int mode, int rot90, float* out, void* stream);
+/* One 16-bit radix pass over fp32 bit patterns (non-negative data) for the exact device-side
+ * np.quantile(., 0.90) of visualizations.py:886: shift 16 = high half, shift 0 = low half of the
+ * elements whose high half equals prefix.  hist uint32 [65536] (zeroed by the call). */
+int ctc_hist16(const float* x, int64_t n, int shift, unsigned int prefix, unsigned int* hist, void* stream);
+/* Integrated-gradients finalisation, second half (visualizations.py:882-901): normalise, zero below the
+ * quantile q, ** 0.05, divide by the new max (inv_m3 = 1/(max+1e-8)), optional rot90. */
+int ctc_ig_finalize(const float* ig, int D, int H, int W, float mn, float mx, float q, float inv_m3, int rot90,
+                    float* out, void* stream);
+/* Occlusion heat map (visualizations.py:366-367, 390-392, 411-413) from per-window importances on the regular
+ * window grid [nd,nh,nw] (window i starts at i*stride); inc uint8 marks evaluated windows; heat = sum/count. */
+int ctc_occlusion_heatmap(const float* imp, const unsigned char* inc, int nd, int nh, int nw, int pd, int ph, int pw,
+                          int sd, int sh, int sw, int D, int H, int W, float* heat, void* stream);
 
 #ifdef __cplusplus
 }

@@ -343,7 +343,8 @@ def encode(tokens: Tensor, sd: Dict[str, Tensor], cfg: CTConfig, capture: Option
     return x.reshape(b, h, w, t, C).permute(0, 3, 1, 2, 4)               # b t h w d
 
 
-def vq_cosine(x: Tensor, codebook: Tensor, grad_mode: str = "ste_l2norm") -> Tuple[Tensor, Tensor]:
+def vq_cosine(x: Tensor, codebook: Tensor, grad_mode: str = "ste_l2norm",
+              force_indices: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """`VectorQuantize(dim, codebook_size, use_cosine_sim=True)` in train() mode with
     freeze_codebook=True (ctvit.py:66,117-118).  Third-party, restated from the published
     algorithm (lucidrains/vector-quantize-pytorch, CosineSimCodebook): x̂ = l2norm(x.float());
@@ -351,12 +352,14 @@ def vq_cosine(x: Tensor, codebook: Tensor, grad_mode: str = "ste_l2norm") -> Tup
     Forward value is E[ind].  Backward (PARITY UNPINNED, see module docstring):
       ste_l2norm : out = x̂ + (E[ind] − x̂).detach()   (releases that normalise first)
       ste_raw    : out = x  + (E[ind] − x ).detach()   (older releases)
-    x: [b, n, d]; codebook: [1, K, d].  Returns (out [b,n,d], ind [b,n] int64)."""
+    x: [b, n, d]; codebook: [1, K, d].  Returns (out [b,n,d], ind [b,n] int64).
+    `force_indices` (test aid, not in the reference) overrides the arg-max so that a comparison
+    can be conditioned on identical code assignments."""
     x = x.float()
     E = codebook[0]
     xh = l2norm(x)
     dist = xh @ E.t()
-    ind = dist.argmax(dim=-1)
+    ind = dist.argmax(dim=-1) if force_indices is None else force_indices.reshape(x.shape[:-1]).long()
     q = E[ind]
     base = xh if grad_mode == "ste_l2norm" else x
     if grad_mode not in ("ste_l2norm", "ste_raw"):
@@ -366,7 +369,7 @@ def vq_cosine(x: Tensor, codebook: Tensor, grad_mode: str = "ste_l2norm") -> Tup
 
 
 def ctvit_forward(image: Tensor, sd: Dict[str, Tensor], cfg: CTConfig,
-                  capture: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
+                  capture: Optional[dict] = None, force_indices: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """CTViT.forward ctvit.py:105-125 (model_type='ctclip').  Returns
     (tokens [b,t,h,w,dim], codebook indices [b, t*h*w])."""
     vt = "visual_transformer."
@@ -378,18 +381,18 @@ def ctvit_forward(image: Tensor, sd: Dict[str, Tensor], cfg: CTConfig,
     flat = tokens.reshape(b, t * h * w, C)
     if capture is not None:
         capture["pre_vq"] = flat
-    q, ind = vq_cosine(flat, sd[vt + "vq._codebook.embed"], cfg.vq_grad_mode)
+    q, ind = vq_cosine(flat, sd[vt + "vq._codebook.embed"], cfg.vq_grad_mode, force_indices)
     if capture is not None:
         capture["vq_features"] = q
     return q.reshape(b, t, h, w, C), ind
 
 
 def ctclip_forward(image: Tensor, text_embeds: Tensor, sd: Dict[str, Tensor], cfg: CTConfig,
-                   capture: Optional[dict] = None):
+                   capture: Optional[dict] = None, force_indices: Optional[Tensor] = None):
     """CTCLIP.forward models/ctclip.py:99-129 on the `text_embeds` path (text tower
     bypassed, :107), world size 1 (gather is the identity, :94-97).
     Returns (sim [B,B], image_latents, text_latents, exp(T), image_tokens, indices)."""
-    tokens, ind = ctvit_forward(image, sd, cfg, capture)
+    tokens, ind = ctvit_forward(image, sd, cfg, capture, force_indices)
     img = tokens.mean(dim=1)                                  # over t  (ctclip.py:111)
     img = img.reshape(img.shape[0], -1)                       # (h w c) (ctclip.py:112)
     text_latents = text_embeds @ sd["to_text_latent.weight"].t()

@@ -11,7 +11,7 @@ def _declared():
     txt = (ROOT / "include" / "ctclip_b200.h").read_text()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(int|const char\*)\s+(ctc_\w+)\s*\(([^;]*?)\)\s*;", txt, flags=re.S):
+    for m in re.finditer(r"\b(int|long long|const char\*)\s+(ctc_\w+)\s*\(([^;]*?)\)\s*;", txt, flags=re.S):
         args = m.group(3).strip()
         n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
         out[m.group(2)] = n

@@ -59,13 +59,17 @@ def test_tiny_forward_backward_vs_oracle(no_tf32, gemm_impl):
     assert relmax(ctx.x_pre_vq, pre) < 3e-2
     agree = float((ctx.indices.long() == ind.reshape(-1)).float().mean())
     assert agree > 0.9, agree
-    # loss = sum of the diagonal (Bt == B)
-    (g_ref,) = torch.autograd.grad(sim.diagonal().sum(), xin)
-    # sims are differences of O(1) cosines: compare absolutely against the logit scale
-    assert float((ctx.sim - sim).abs().max()) < 3e-2 * float(sim.abs().max().clamp_min(0.1))
-    if agree == 1.0:
-        assert pearson(grad, g_ref) > 0.99
-        assert relmax(grad, g_ref) < 0.1
+    # A 216-token model makes every flipped near-tie code visible in the logits, so condition the
+    # remaining comparison on identical code assignments (oracle re-run with OUR indices).
+    sim_f, il_f, _, _, tok_f, _ = O.ctclip_forward(xin, txt, sd, cfg, None, force_indices=ctx.indices)
+    assert float((ctx.tokens - tok_f.reshape(-1, cfg.dim).detach()).abs().max()) < 1e-6
+    assert float((ctx.sim - sim_f).abs().max()) < 2e-3
+    assert relmax(ctx.image_latents, il_f) < 2e-3
+    (g_ref,) = torch.autograd.grad(sim_f.diagonal().sum(), xin)
+    print(f"\n[tiny impl={gemm_impl}] code agreement {agree:.4f} grad pearson {pearson(grad, g_ref):.5f} "
+          f"rel.err {relmax(grad, g_ref):.3e}")
+    assert pearson(grad, g_ref) > 0.995
+    assert relmax(grad, g_ref) < 5e-2
 
 
 def test_full_forward_vs_oracle_and_golden(no_tf32, golden_dir):
@@ -114,12 +118,13 @@ def test_full_backward_vs_oracle(no_tf32):
     grad = eng.backward(ctx)
     torch.cuda.synchronize()
     xa = (1 + 0.5 * (vol - 1)).detach().requires_grad_()
-    sim = O.ctclip_forward(xa, txt, sd, cfg)[0]
+    sim = O.ctclip_forward(xa, txt, sd, cfg, None, force_indices=ctx.indices)[0]
     (g_ref,) = torch.autograd.grad(sim[0, 0], xa)
-    # token-level aggregation (sum over each patch) is the robust comparison quantity
-    tok = lambda g: g.reshape(24, 10, 24, 20, 24, 20).sum(dim=(1, 3, 5))
+    # (LN(4000) is invariant to an affine change of the patch, so per-patch sums of g and of g*x vanish
+    # identically: only voxel-level and per-token-energy comparisons are meaningful.)
+    tok = lambda g: g.reshape(24, 10, 24, 20, 24, 20).square().sum(dim=(1, 3, 5)).sqrt()
     pt, pr = pearson(tok(grad), tok(g_ref)), pearson(grad, g_ref)
-    print(f"\n[full bwd] sim {float(ctx.sim):.6f} vs {float(sim):.6f}; grad pearson voxel {pr:.5f} token {pt:.5f}; "
+    print(f"\n[full bwd] sim {float(ctx.sim):.6f} vs {float(sim):.6f}; grad pearson voxel {pr:.5f} token-energy {pt:.5f}; "
           f"rel.err {relmax(grad, g_ref):.3e}")
     assert pr > 0.98
-    assert pt > 0.98
+    assert pt > 0.99

@@ -1,0 +1,84 @@
+"""CPU: host-side sharding logic (window / alpha-step partition) including the world_size-2 gloo path."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from hypothesis import given, settings, strategies as st
+
+from oracle import ctclip_oracle as O
+
+
+def _attr():
+    from ctclip_b200 import attribution
+    return attribution
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 400), st.integers(1, 9), st.booleans())
+def test_shard_range_properties(total, world, parity):
+    A = _attr()
+    ranges = [A.shard_range(total, r, world, parity) for r in range(world)]
+    covered = [i for s, e in ranges for i in range(s, e)]
+    assert covered == sorted(set(covered))                        # disjoint, ordered, contiguous per rank
+    if parity:   # reference semantics: total // world each, remainder dropped (visualizations.py:351-361)
+        assert all(e - s == total // world for s, e in ranges)
+        assert len(covered) == (total // world) * world
+        windows = list(range(total))
+        for r in range(world):
+            assert windows[ranges[r][0]:ranges[r][1]] == O.shard_windows(windows, r, world)
+    else:
+        assert covered == list(range(total))
+        assert max(e - s for s, e in ranges) - min(e - s for s, e in ranges) <= 1
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.tuples(st.integers(4, 40), st.integers(4, 40), st.integers(4, 40)),
+       st.tuples(st.integers(1, 8), st.integers(1, 8), st.integers(1, 8)),
+       st.tuples(st.integers(1, 5), st.integers(1, 5), st.integers(1, 5)))
+def test_window_enumeration_matches_oracle(shape, patch, stride):
+    A = _attr()
+    patch = tuple(min(p, s) for p, s in zip(patch, shape))
+    assert A.occlusion_windows(shape, patch, stride) == O.occlusion_windows(shape, patch, stride)
+
+
+def test_default_window_grid():
+    A = _attr()
+    w = A.occlusion_windows((240, 480, 480))
+    assert len(w) == 12167 and w[:3] == [(0, 0, 0), (0, 0, 20), (0, 0, 40)] and w[-1] == (220, 440, 440)
+
+
+def _worker(rank, world, port, total, parity, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A = _attr()
+    s, e = A.shard_range(total, rank, world, parity)
+    local = torch.arange(s, e, dtype=torch.float32) * 0.5 + 1.0       # stand-in per-window scores
+    scores, inc = A.combine_sharded(local, s, e, total)
+    # IG partial sums: each rank owns a slice of steps, the all-reduce restores the full sum
+    s2, e2 = A.shard_range(50, rank, world, False)
+    part = torch.tensor([float(sum(range(s2, e2)))])
+    dist.all_reduce(part)
+    q.put((rank, scores.tolist(), inc.tolist(), float(part)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("parity", [True, False])
+def test_world2_gloo_combine(parity):
+    world, total = 2, 27
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, parity, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    kept = (total // world) * world if parity else total
+    for rank, scores, inc, part in res:
+        assert inc == [1] * kept + [0] * (total - kept)
+        assert scores[:kept] == [i * 0.5 + 1.0 for i in range(kept)] and all(v == 0 for v in scores[kept:])
+        assert part == float(sum(range(50)))
