@@ -574,9 +574,9 @@ static int fill_params(AttnParams& p, int B, int T, int H, int W, int heads, int
     return 0;
 }
 
-template <typename Kern>
-static int launch_attn(Kern kern, const AttnParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;   // one static per kernel instantiation
+template <void (*kern)(const AttnParams)>
+static int launch_attn(const AttnParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;   // one static per kernel (the kernel is a non-type template argument)
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -594,16 +594,16 @@ static int run_fwd(AttnParams& p, cudaStream_t st) {
     const size_t nb = p.bias_table ? (size_t)(2 * p.H - 1) * (2 * p.W - 1) : 0;
     const size_t smem = (size_t)HPC * (p.n_pad * 128 + QB * 64) + 256 + p.n_pad * 4 + nb * 4;
     dim3 grid(p.n_seq, p.heads / HPC, (p.n + QB - 1) / QB);
-    return launch_attn(attn_fwd_kernel<QB, KBLK, HPC, PROBS>, p, grid, HPC * (QB / 16) * 32, smem, st);
+    return launch_attn<attn_fwd_kernel<QB, KBLK, HPC, PROBS>>(p, grid, HPC * (QB / 16) * 32, smem, st);
 }
 template <int QB, int KBLK, int HPC>
 static int run_bwd(AttnParams& p, cudaStream_t st) {
     const size_t nb = p.bias_table ? (size_t)(2 * p.H - 1) * (2 * p.W - 1) : 0;
     dim3 grid(p.n_seq, p.heads / HPC, (p.n + QB - 1) / QB);
     const size_t smem_dq = (size_t)HPC * (p.n_pad * 128 + 2 * QB * 64 + QB * 4) + 256 + p.n_pad * 4 + nb * 4;
-    if (int e = launch_attn(attn_bwd_dq_kernel<QB, KBLK, HPC>, p, grid, HPC * (QB / 16) * 32, smem_dq, st)) return e;
+    if (int e = launch_attn<attn_bwd_dq_kernel<QB, KBLK, HPC>>(p, grid, HPC * (QB / 16) * 32, smem_dq, st)) return e;
     const size_t smem_dkv = (size_t)HPC * (p.n_pad * 128 + 2 * QB * 64 + 2 * p.n_pad * 4) + 256 + p.n_pad * 4 + nb * 4;
-    return launch_attn(attn_bwd_dkv_kernel<QB, KBLK, HPC>, p, grid, HPC * (QB / 16) * 32, smem_dkv, st);
+    return launch_attn<attn_bwd_dkv_kernel<QB, KBLK, HPC>>(p, grid, HPC * (QB / 16) * 32, smem_dkv, st);
 }
 
 }  // namespace ctc

@@ -30,29 +30,44 @@ CTC_DEVINL float perturb(float v, int d, int y, int x, float alpha, bool has_alp
 // Shared-memory tile: [pt*p rows][G*p floats] (the CTA's G patches side by side along W).
 // All index arithmetic in the hot loops is incremental (no integer division per element).
 
-// per-patch mean / rstd with the two-pass formula; thread -> fixed tile column, strided rows
-CTC_DEVINL void patch_stats(const float* tile, const PatchGeom& g, int rows, int rowlen, float eps, float* s_acc,
-                            float* s_mean, float* s_rstd) {
+// Deterministic per-patch reduction: thread -> fixed tile column (hence fixed patch), strided rows; the
+// per-thread partials are combined by ONE thread per patch in a fixed order (no floating-point atomics, so
+// two runs give bit-identical statistics — the VQ arg-max downstream amplifies last-bit noise).
+template <class F>
+CTC_DEVINL void patch_reduce2(const PatchGeom& g, int rows, int rowlen, float* s_part, float* out0, float* out1, F f) {
     const int rg = blockDim.x / rowlen;                  // row groups (rowlen <= blockDim.x by construction)
     const int col = threadIdx.x % rowlen, r0 = threadIdx.x / rowlen;
-    const int j = col / g.p;
-    const bool active = r0 < rg;
-    if (threadIdx.x < 32) s_acc[threadIdx.x] = 0.f;
+    float a0 = 0.f, a1 = 0.f;
+    if (r0 < rg)
+        for (int r = r0; r < rows; r += rg) { const float2 v = f(r, col); a0 += v.x; a1 += v.y; }
+    s_part[threadIdx.x] = a0;
+    s_part[blockDim.x + threadIdx.x] = a1;
     __syncthreads();
-    float s = 0.f;
-    if (active) for (int r = r0; r < rows; r += rg) s += tile[r * rowlen + col];
-    if (active) atomicAdd(&s_acc[j], s);
+    if (threadIdx.x < g.G) {
+        float t0 = 0.f, t1 = 0.f;
+        for (int q = 0; q < rg; ++q)
+            for (int c = 0; c < g.p; ++c) {
+                const int i = q * rowlen + threadIdx.x * g.p + c;
+                t0 += s_part[i]; t1 += s_part[blockDim.x + i];
+            }
+        out0[threadIdx.x] = t0;
+        if (out1) out1[threadIdx.x] = t1;
+    }
     __syncthreads();
-    if (threadIdx.x < g.G) s_mean[threadIdx.x] = s_acc[threadIdx.x] / g.P;
+}
+
+// per-patch mean / rstd with the two-pass formula
+CTC_DEVINL void patch_stats(const float* tile, const PatchGeom& g, int rows, int rowlen, float eps, float* s_part,
+                            float* s_mean, float* s_rstd) {
+    patch_reduce2(g, rows, rowlen, s_part, s_mean, nullptr,
+                  [&](int r, int col) { return make_float2(tile[r * rowlen + col], 0.f); });
+    if (threadIdx.x < g.G) s_mean[threadIdx.x] /= g.P;
     __syncthreads();
-    if (threadIdx.x < 32) s_acc[threadIdx.x] = 0.f;
-    __syncthreads();
-    const float mean = s_mean[j];
-    float q = 0.f;
-    if (active) for (int r = r0; r < rows; r += rg) { const float d = tile[r * rowlen + col] - mean; q += d * d; }
-    if (active) atomicAdd(&s_acc[j], q);
-    __syncthreads();
-    if (threadIdx.x < g.G) s_rstd[threadIdx.x] = rsqrtf(s_acc[threadIdx.x] / g.P + eps);
+    patch_reduce2(g, rows, rowlen, s_part, s_rstd, nullptr, [&](int r, int col) {
+        const float d = tile[r * rowlen + col] - s_mean[col / g.p];
+        return make_float2(d * d, 0.f);
+    });
+    if (threadIdx.x < g.G) s_rstd[threadIdx.x] = rsqrtf(s_rstd[threadIdx.x] / g.P + eps);
     __syncthreads();
 }
 
@@ -80,7 +95,7 @@ patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
                        const float* __restrict__ beta, float eps, const float* __restrict__ alpha,
                        const int* __restrict__ occl, float oval, __nv_bfloat16* __restrict__ out) {
     extern __shared__ float tile[];
-    __shared__ float s_mean[32], s_rstd[32], s_acc[32];
+    __shared__ float s_mean[32], s_rstd[32], s_part[512];
     const int groups_w = g.Wp / g.G;
     int bid = blockIdx.x;
     const int gw = bid % groups_w; bid /= groups_w;
@@ -128,7 +143,7 @@ patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
         }
         __syncthreads();
     }
-    patch_stats(tile, g, rows, rowlen, eps, s_acc, s_mean, s_rstd);
+    patch_stats(tile, g, rows, rowlen, eps, s_part, s_mean, s_rstd);
     // ---- normalise + affine, write bf16 rows; consecutive threads write consecutive pairs of a patch row
     const long long tok0 = (((long long)b * g.T + tp) * g.Hp + hp) * g.Wp + (long long)gw * g.G;
     PairIter it; it.init(g, rows);
@@ -152,7 +167,7 @@ patchify_ln_bwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
                        const float* __restrict__ alpha, const __nv_bfloat16* __restrict__ dy,
                        float* __restrict__ grad, int sum_over_batch, float wscale) {
     extern __shared__ float tile[];
-    __shared__ float s_mean[32], s_rstd[32], s_acc[32], s_mg[32], s_mgx[32];
+    __shared__ float s_mean[32], s_rstd[32], s_part[512], s_mg[32], s_mgx[32];
     const int groups_w = g.Wp / g.G;
     int bid = blockIdx.x;
     const int gw = bid % groups_w; bid /= groups_w;
@@ -188,29 +203,13 @@ patchify_ln_bwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
         for (int i = threadIdx.x; i < rows * rowlen; i += blockDim.x) tile[i] = 1.f + a * (tile[i] - 1.f);
         __syncthreads();
     }
-    patch_stats(tile, g, rows, rowlen, eps, s_acc, s_mean, s_rstd);
-    // ---- per-patch mean(g) and mean(g * xhat): patch-major walk (coalesced dY reads), flush on patch change
-    if (threadIdx.x < 32) { s_mg[threadIdx.x] = 0.f; s_mgx[threadIdx.x] = 0.f; }
-    __syncthreads();
-    {
-        PairIter it; it.init(g, rows);
-        float sg = 0.f, sgx = 0.f;
-        int cur = it.j;
-        while (it.j < g.G) {
-            if (it.j != cur) { atomicAdd(&s_mg[cur], sg); atomicAdd(&s_mgx[cur], sgx); sg = sgx = 0.f; cur = it.j; }
-            const int e = it.r * g.p + it.c;
-            const float mean = s_mean[it.j], rstd = s_rstd[it.j];
-            const float2 v = *reinterpret_cast<const float2*>(tile + it.r * rowlen + it.j * g.p + it.c);
-            const float2 gm = *reinterpret_cast<const float2*>(gamma + e);
-            const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dys + it.j * g.P + e));
-            const float g0 = d.x * gm.x, g1 = d.y * gm.y;
-            sg += g0 + g1;
-            sgx += g0 * (v.x - mean) * rstd + g1 * (v.y - mean) * rstd;
-            it.next();
-        }
-        if (cur < g.G) { atomicAdd(&s_mg[cur], sg); atomicAdd(&s_mgx[cur], sgx); }
-    }
-    __syncthreads();
+    patch_stats(tile, g, rows, rowlen, eps, s_part, s_mean, s_rstd);
+    // ---- per-patch sum(g) and sum(g * xhat), g = dY * gamma (dY tile is in shared memory)
+    patch_reduce2(g, rows, rowlen, s_part, s_mg, s_mgx, [&](int r, int col) {
+        const int j = col / g.p, e = r * g.p + (col - j * g.p);
+        const float gg = __bfloat162float(dys[j * g.P + e]) * gamma[e];
+        return make_float2(gg, gg * (tile[r * rowlen + col] - s_mean[j]) * s_rstd[j]);
+    });
     // ---- dx in place of x (same tile positions), then store coalesced along W
     {
         PairIter it; it.init(g, rows);

@@ -104,14 +104,22 @@ def kth_value(x: torch.Tensor, k: int) -> float:
 
 
 def quantile_linear(x: torch.Tensor, q: float) -> float:
-    """np.quantile(x, q) (linear interpolation, fp32 result) computed on the device."""
+    """np.quantile(x, q) for an fp32 tensor, evaluated on the device and bit-identical to NumPy 2.x:
+    NumPy casts a Python-float q to the array dtype, so the virtual index (n-1)*q, the interpolation
+    weight and the lerp are all float32 (at n = 55 296 000 the fp32 index is already an integer)."""
     n = x.numel()
-    pos = q * (n - 1)
-    lo = int(math.floor(pos))
-    frac = pos - lo
-    a = kth_value(x, lo)
-    b = kth_value(x, min(lo + 1, n - 1)) if frac > 0 else a
-    return float(np.float32(a + (b - a) * frac))
+    qf = np.asanyarray(q, dtype=np.float32)
+    vi = (n - 1) * qf
+    prev = int(np.floor(vi))
+    nxt = min(prev + 1, n - 1)
+    gamma = np.asanyarray(vi - np.float32(prev), dtype=np.float32)
+    a = np.float32(kth_value(x, prev))
+    b = np.float32(kth_value(x, nxt)) if gamma > 0 else a
+    d = np.subtract(b, a)
+    r = np.add(a, d * gamma)
+    if gamma >= 0.5:
+        r = np.subtract(b, d * (1 - gamma))
+    return float(np.float32(r))
 
 
 # ------------------------------------------------------------------------------------------- occlusion

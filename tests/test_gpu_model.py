@@ -64,7 +64,7 @@ def test_tiny_forward_backward_vs_oracle(no_tf32, gemm_impl):
     sim_f, il_f, _, _, tok_f, _ = O.ctclip_forward(xin, txt, sd, cfg, None, force_indices=ctx.indices)
     assert float((ctx.tokens - tok_f.reshape(-1, cfg.dim).detach()).abs().max()) < 1e-6
     assert float((ctx.sim - sim_f).abs().max()) < 2e-3
-    assert relmax(ctx.image_latents, il_f) < 2e-3
+    assert relmax(ctx.image_latents, il_f) < 5e-3
     (g_ref,) = torch.autograd.grad(sim_f.diagonal().sum(), xin)
     print(f"\n[tiny impl={gemm_impl}] code agreement {agree:.4f} grad pearson {pearson(grad, g_ref):.5f} "
           f"rel.err {relmax(grad, g_ref):.3e}")
