@@ -119,70 +119,103 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 // ---------------------------------------------------------------------------------------------
 static constexpr int PEG_TT = 2, PEG_TH = 8;
 
+// One output column.  A,B,D are the register columns holding x[w-1], x[w], x[w+1] for the 9 (dt,dh) rows;
+// N is the column slot being (re)filled with x[w+4] (three columns stay in flight: w+2, w+3, w+4).
+// With the 6-slot rotation fully unrolled no register moves remain, and with a compile-time channel count
+// every load/store of an unrolled block is "base register + immediate".
+#define PEG_STEP(A, B, D, N, WOFF, LOADCOL)                                                        \
+    {                                                                                                \
+        const int wc = w0 + (WOFF);                                                                  \
+        if (LOADCOL) {                                                                               \
+            _Pragma("unroll") for (int k9 = 0; k9 < 9; ++k9) N[k9] = rp[k9][(long long)(wc + 4) * CS]; \
+        } else {                                                                                     \
+            _Pragma("unroll") for (int k9 = 0; k9 < 9; ++k9) N[k9] = 0.f;                            \
+        }                                                                                            \
+        float acc = B[7] + bv, acc1 = 0.f, acc2 = 0.f;                                               \
+        _Pragma("unroll") for (int k9 = 0; k9 < 9; ++k9) {                                           \
+            acc = fmaf(wk[k9][0], A[k9], acc);                                                       \
+            acc1 = fmaf(wk[k9][1], B[k9], acc1);                                                     \
+            acc2 = fmaf(wk[k9][2], D[k9], acc2);                                                     \
+        }                                                                                            \
+        acc += acc1 + acc2;                                                                          \
+        yo[(long long)wc * CS] = acc;                                                                \
+        if (BF16OUT) yb[(long long)wc * CS] = __float2bfloat16(acc);                                 \
+    }
+
+// CC = compile-time channel count (0: runtime); SIGN = +1 forward, -1 adjoint; BF16OUT = also emit a bf16 copy
+template <int CC, int SIGN, bool BF16OUT>
 __global__ void __launch_bounds__(PEG_TT * PEG_TH * 32)
 peg_kernel(const float* __restrict__ x, int B, int T, int H, int W, int C, const float* __restrict__ w27,
-           const float* __restrict__ bias, int mode, int sign, float* __restrict__ y,
-           __nv_bfloat16* __restrict__ y_bf16) {
+           const float* __restrict__ bias, int mode, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16) {
+    constexpr int sign = SIGN;
+    const int CS = CC ? CC : C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     const int h = blockIdx.y * PEG_TH + (warp % PEG_TH);
     const int tiles_t = (T + PEG_TT - 1) / PEG_TT;
     const int t = (blockIdx.z % tiles_t) * PEG_TT + warp / PEG_TH;
     const int b = blockIdx.z / tiles_t;
-    if (h >= H || t >= T || c >= C) return;
-    // weights: wk[k9][cw] for the 9 non-w taps x 3 w taps
+    if (h >= H || t >= T || c >= CS) return;
+    // weights wk[k9][cw] for the 9 non-w taps x 3 w taps; rows outside the grid alias the centre row with
+    // zero weights, so that every load of the main loop is unconditional
     float wk[9][3];
-    const float* rowp[9];
+    const float* rp[9];
+    const float* self = x + ((((long long)b * T + t) * H + h) * W) * CS + c;
 #pragma unroll
     for (int k9 = 0; k9 < 9; ++k9) {
         const int p = k9 / 3, q = k9 % 3;
         int dt, dh;
         if (mode == CTC_MODE_SPATIAL) { dt = p - 2; dh = q - 1; } else { dh = p - 2; dt = q - 1; }
+        const int tt = t + sign * dt, hh = h + sign * dh;
+        const bool valid = tt >= 0 && tt < T && hh >= 0 && hh < H;
 #pragma unroll
         for (int cw = 0; cw < 3; ++cw) {
-            const int tap = (mode == CTC_MODE_SPATIAL) ? (p * 3 + q) * 3 + cw : (p * 3 + cw) * 3 + q;
-            wk[k9][cw] = w27[tap * C + c];
+            // the adjoint reads x[w - (cw - 1)]: store its w-taps mirrored so that the step body is identical
+            const int cwm = (SIGN > 0) ? cw : 2 - cw;
+            const int tap = (mode == CTC_MODE_SPATIAL) ? (p * 3 + q) * 3 + cwm : (p * 3 + cwm) * 3 + q;
+            wk[k9][cw] = valid ? w27[tap * CS + c] : 0.f;
         }
-        const int tt = t + sign * dt, hh = h + sign * dh;
-        rowp[k9] = (tt >= 0 && tt < T && hh >= 0 && hh < H)
-                       ? x + ((((long long)b * T + tt) * H + hh) * W) * C + c : nullptr;
+        rp[k9] = valid ? x + ((((long long)b * T + tt) * H + hh) * W) * CS + c : self;
     }
     const float bv = (bias && sign > 0) ? bias[c] : 0.f;
-    // register window: columns w-1, w, w+1, plus column w+2 already in flight (`pre`); the loads issued in
-    // iteration w (column w+3) are first consumed two iterations later, which hides the L2 latency
-    float win[9][3], pre[9];
-    const long long cs = C;
+    float* yo = y + (self - x);
+    __nv_bfloat16* yb = BF16OUT ? y_bf16 + (self - x) : nullptr;
+    // k9 = 7 is the (dt, dh) = (0, 0) row: B[7] is the residual term x[w] (its weights are always valid)
+    float c0[9], c1[9], c2[9], c3[9], c4[9], c5[9];
 #pragma unroll
     for (int k9 = 0; k9 < 9; ++k9) {
-        win[k9][0] = 0.f;
-        win[k9][1] = rowp[k9] ? rowp[k9][0] : 0.f;
-        win[k9][2] = (rowp[k9] && W > 1) ? rowp[k9][cs] : 0.f;
-        pre[k9] = (rowp[k9] && W > 2) ? rowp[k9][2 * cs] : 0.f;
+        c0[k9] = 0.f;                                          // x[-1]
+        c1[k9] = rp[k9][0];
+        c2[k9] = (W > 1) ? rp[k9][(long long)1 * CS] : 0.f;
+        c3[k9] = (W > 2) ? rp[k9][(long long)2 * CS] : 0.f;
+        c4[k9] = (W > 3) ? rp[k9][(long long)3 * CS] : 0.f;
+        c5[k9] = 0.f;
     }
-    const long long out_base = ((((long long)b * T + t) * H + h) * W) * C + c;
-    for (int w = 0; w < W; ++w) {
-        float ld[9];
-        const bool more = (w + 3 < W);
-#pragma unroll
-        for (int k9 = 0; k9 < 9; ++k9) ld[k9] = (more && rowp[k9]) ? rowp[k9][(long long)(w + 3) * cs] : 0.f;
-        float acc = win[7][1] + bv;   // k9 = 7 is the (dt, dh) = (0, 0) row: the residual term
-#pragma unroll
-        for (int k9 = 0; k9 < 9; ++k9) {
-            // forward: tap cw reads x[w + cw - 1]; adjoint: x[w - (cw - 1)]
-            if (sign > 0) acc += wk[k9][0] * win[k9][0] + wk[k9][1] * win[k9][1] + wk[k9][2] * win[k9][2];
-            else          acc += wk[k9][2] * win[k9][0] + wk[k9][1] * win[k9][1] + wk[k9][0] * win[k9][2];
+    int w0 = 0;
+    for (; w0 + 6 + 4 <= W; w0 += 6) {          // every column w0+4 .. w0+9 is inside the row: unconditional loads
+        PEG_STEP(c0, c1, c2, c5, 0, true)
+        PEG_STEP(c1, c2, c3, c0, 1, true)
+        PEG_STEP(c2, c3, c4, c1, 2, true)
+        PEG_STEP(c3, c4, c5, c2, 3, true)
+        PEG_STEP(c4, c5, c0, c3, 4, true)
+        PEG_STEP(c5, c0, c1, c4, 5, true)
+    }
+    for (; w0 < W; w0 += 6) {                   // tail block(s): guard loads and stores
+#define PEG_TAIL(A, B, D, N, WOFF)                                     \
+        if (w0 + (WOFF) < W) {                                         \
+            if (w0 + (WOFF) + 4 < W) PEG_STEP(A, B, D, N, WOFF, true)  \
+            else PEG_STEP(A, B, D, N, WOFF, false)                     \
         }
-        y[out_base + (long long)w * cs] = acc;
-        if (y_bf16) y_bf16[out_base + (long long)w * cs] = __float2bfloat16(acc);
-#pragma unroll
-        for (int k9 = 0; k9 < 9; ++k9) {
-            win[k9][0] = win[k9][1];
-            win[k9][1] = win[k9][2];
-            win[k9][2] = pre[k9];
-            pre[k9] = ld[k9];
-        }
+        PEG_TAIL(c0, c1, c2, c5, 0)
+        PEG_TAIL(c1, c2, c3, c0, 1)
+        PEG_TAIL(c2, c3, c4, c1, 2)
+        PEG_TAIL(c3, c4, c5, c2, 3)
+        PEG_TAIL(c4, c5, c0, c3, 4)
+        PEG_TAIL(c5, c0, c1, c4, 5)
+#undef PEG_TAIL
     }
 }
+#undef PEG_STEP
 
 // ---------------------------------------------------------------------------------------------
 // GEGLU
@@ -294,8 +327,18 @@ extern "C" int ctc_peg(const float* x, int B, int T, int H, int W, int C, const 
     const int tiles_t = (T + PEG_TT - 1) / PEG_TT;
     CTC_REQUIRE((long long)B * tiles_t <= 65535, "peg: batch %d too large for one launch", B);
     dim3 grid((C + 31) / 32, (H + PEG_TH - 1) / PEG_TH, B * tiles_t);
-    peg_kernel<<<grid, PEG_TT * PEG_TH * 32, 0, (cudaStream_t)stream>>>(
-        x, B, T, H, W, C, w27, bias, mode, transpose ? -1 : 1, y, (__nv_bfloat16*)y_bf16);
+    const int threads = PEG_TT * PEG_TH * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16* yb = (__nv_bfloat16*)y_bf16;
+#define PEG_LAUNCH(CC, SG, BF) peg_kernel<CC, SG, BF><<<grid, threads, 0, st>>>(x, B, T, H, W, C, w27, bias, mode, y, yb)
+    if (C == 512) {
+        if (!transpose) { if (yb) PEG_LAUNCH(512, 1, true); else PEG_LAUNCH(512, 1, false); }
+        else            { if (yb) PEG_LAUNCH(512, -1, true); else PEG_LAUNCH(512, -1, false); }
+    } else {
+        if (!transpose) { if (yb) PEG_LAUNCH(0, 1, true); else PEG_LAUNCH(0, 1, false); }
+        else            { if (yb) PEG_LAUNCH(0, -1, true); else PEG_LAUNCH(0, -1, false); }
+    }
+#undef PEG_LAUNCH
     CTC_LAUNCH_CHECK();
     return 0;
 }

@@ -171,9 +171,12 @@ struct Top2 {
     float v0, v1;
     int i0, i1;
     CTC_DEVINL void init() { v0 = v1 = -3.0e38f; i0 = i1 = 0; }
-    CTC_DEVINL void push(float v, int i) {
-        if (v > v0) { v1 = v0; i1 = i0; v0 = v; i0 = i; }
-        else if (v > v1) { v1 = v; i1 = i; }
+    CTC_DEVINL void push(float v, int i) {   // branch-free: 2 compares + 6 selects
+        const bool g0 = v > v0, g1 = v > v1;
+        v1 = g0 ? v0 : (g1 ? v : v1);
+        i1 = g0 ? i0 : (g1 ? i : i1);
+        v0 = g0 ? v : v0;
+        i0 = g0 ? i : i0;
     }
 };
 

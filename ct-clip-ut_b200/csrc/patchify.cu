@@ -28,67 +28,83 @@ CTC_DEVINL float perturb(float v, int d, int y, int x, float alpha, bool has_alp
 }
 
 // Shared-memory tile: [pt*p rows][G*p floats] (the CTA's G patches side by side along W).
-// All index arithmetic in the hot loops is incremental (no integer division per element).
+// Every pass walks the tile with the same "quad" mapping: thread -> (column quad cq, row group), i.e. one
+// 128-bit shared-memory access per 4 voxels of ONE patch (p % 4 == 0) and no per-element index arithmetic.
+struct QuadMap {
+    int ncq, rgq, cq, rgi, j, c;      // column quads per row, row groups, my quad, my row group, my patch, col in patch
+    bool active;
+    CTC_DEVINL void init(const PatchGeom& g, int rowlen) {
+        ncq = rowlen >> 2;
+        rgq = blockDim.x / ncq;
+        cq = threadIdx.x % ncq; rgi = threadIdx.x / ncq;
+        active = rgi < rgq;
+        j = (cq * 4) / g.p;
+        c = cq * 4 - j * g.p;
+    }
+};
 
-// Deterministic per-patch reduction: thread -> fixed tile column (hence fixed patch), strided rows; the
-// per-thread partials are combined by ONE thread per patch in a fixed order (no floating-point atomics, so
+// Deterministic per-patch reduction of two per-thread partials (fixed shuffle tree, no floating-point atomics:
 // two runs give bit-identical statistics — the VQ arg-max downstream amplifies last-bit noise).
-template <class F>
-CTC_DEVINL void patch_reduce2(const PatchGeom& g, int rows, int rowlen, float* s_part, float* out0, float* out1, F f) {
-    const int rg = blockDim.x / rowlen;                  // row groups (rowlen <= blockDim.x by construction)
-    const int col = threadIdx.x % rowlen, r0 = threadIdx.x / rowlen;
-    float a0 = 0.f, a1 = 0.f;
-    if (r0 < rg)
-        for (int r = r0; r < rows; r += rg) { const float2 v = f(r, col); a0 += v.x; a1 += v.y; }
-    s_part[threadIdx.x] = a0;
-    s_part[blockDim.x + threadIdx.x] = a1;
+CTC_DEVINL void patch_reduce2(const PatchGeom& g, const QuadMap& m, float a0, float a1, float* s_part, float* out0,
+                              float* out1) {
+    // s_part layout: [2][rgq][ncq]
+    const int n = m.rgq * m.ncq;
+    if (m.active) { s_part[m.rgi * m.ncq + m.cq] = a0; s_part[n + m.rgi * m.ncq + m.cq] = a1; }
     __syncthreads();
-    if (threadIdx.x < g.G) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qpp = g.p >> 2;                             // quads per patch row
+    for (int j = warp; j < g.G; j += blockDim.x >> 5) {
         float t0 = 0.f, t1 = 0.f;
-        for (int q = 0; q < rg; ++q)
-            for (int c = 0; c < g.p; ++c) {
-                const int i = q * rowlen + threadIdx.x * g.p + c;
-                t0 += s_part[i]; t1 += s_part[blockDim.x + i];
-            }
-        out0[threadIdx.x] = t0;
-        if (out1) out1[threadIdx.x] = t1;
+        for (int i = lane; i < m.rgq * qpp; i += 32) {
+            const int idx = (i / qpp) * m.ncq + j * qpp + i % qpp;
+            t0 += s_part[idx]; t1 += s_part[n + idx];
+        }
+        t0 = warp_sum(t0); t1 = warp_sum(t1);
+        if (lane == 0) { out0[j] = t0; if (out1) out1[j] = t1; }
     }
     __syncthreads();
 }
 
 // per-patch mean / rstd with the two-pass formula
-CTC_DEVINL void patch_stats(const float* tile, const PatchGeom& g, int rows, int rowlen, float eps, float* s_part,
-                            float* s_mean, float* s_rstd) {
-    patch_reduce2(g, rows, rowlen, s_part, s_mean, nullptr,
-                  [&](int r, int col) { return make_float2(tile[r * rowlen + col], 0.f); });
+CTC_DEVINL void patch_stats(const float* tile, const PatchGeom& g, const QuadMap& m, int rows, int rowlen, float eps,
+                            float* s_part, float* s_mean, float* s_rstd) {
+    float s = 0.f;
+    if (m.active)
+        for (int r = m.rgi; r < rows; r += m.rgq) {
+            const float4 v = *reinterpret_cast<const float4*>(tile + r * rowlen + m.cq * 4);
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    patch_reduce2(g, m, s, 0.f, s_part, s_mean, nullptr);
     if (threadIdx.x < g.G) s_mean[threadIdx.x] /= g.P;
     __syncthreads();
-    patch_reduce2(g, rows, rowlen, s_part, s_rstd, nullptr, [&](int r, int col) {
-        const float d = tile[r * rowlen + col] - s_mean[col / g.p];
-        return make_float2(d * d, 0.f);
-    });
+    float q = 0.f;
+    if (m.active) {
+        const float mean = s_mean[m.j];
+        for (int r = m.rgi; r < rows; r += m.rgq) {
+            const float4 v = *reinterpret_cast<const float4*>(tile + r * rowlen + m.cq * 4);
+            const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    patch_reduce2(g, m, q, 0.f, s_part, s_rstd, nullptr);
     if (threadIdx.x < g.G) s_rstd[threadIdx.x] = rsqrtf(s_rstd[threadIdx.x] / g.P + eps);
     __syncthreads();
 }
 
-// iterator over (patch j, tile row r, column c) for element pairs in patch-major order e = r*p + c
-struct PairIter {
-    int j, r, c, step_r, step_c, rows, p;
-    CTC_DEVINL void init(const PatchGeom& g, int rows_) {
-        rows = rows_; p = g.p;
-        const int e0 = 2 * threadIdx.x;                   // first pair of this thread (global pair index * 2)
-        j = e0 / g.P;
-        const int e = e0 % g.P;
-        r = e / p; c = e % p;
-        const int stride = 2 * blockDim.x;
-        step_r = stride / p; step_c = stride % p;
+// async tile load: every thread issues all of its 16-byte copies back to back (coalesced along W)
+CTC_DEVINL void load_tile_async(float* tile, const float* vb, const PatchGeom& g, int tp, int hp, int x0, int rows,
+                                int rowlen) {
+    const int vec_per_row = rowlen >> 2;
+    int r = threadIdx.x / vec_per_row, v = threadIdx.x % vec_per_row;
+    const int dr = blockDim.x / vec_per_row, dv = blockDim.x % vec_per_row;
+    while (r < rows) {
+        const int pt_i = r / g.p;
+        const int d = tp * g.pt + pt_i, y = hp * g.p + (r - pt_i * g.p);
+        cp_async_16(tile + r * rowlen + v * 4, vb + ((long long)d * g.H + y) * g.W + x0 + v * 4);
+        v += dv; r += dr;
+        if (v >= vec_per_row) { v -= vec_per_row; ++r; }
     }
-    CTC_DEVINL void next() {
-        c += step_c; r += step_r;
-        if (c >= p) { c -= p; ++r; }
-        while (r >= rows) { r -= rows; ++j; }
-    }
-};
+}
 
 __global__ void __launch_bounds__(256)
 patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* __restrict__ gamma,
@@ -109,19 +125,7 @@ patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
     const float a = has_alpha ? alpha[b] : 1.f;
     const int* oc = occl ? occl + b * 6 : nullptr;
     const int x0 = gw * rowlen;
-    // ---- load: every thread issues all of its 16-byte async copies back to back (coalesced along W)
-    const int vec_per_row = rowlen >> 2;
-    {
-        int r = threadIdx.x / vec_per_row, v = threadIdx.x % vec_per_row;
-        const int dr = blockDim.x / vec_per_row, dv = blockDim.x % vec_per_row;
-        while (r < rows) {
-            const int pt_i = r / g.p;
-            const int d = tp * g.pt + pt_i, y = hp * g.p + (r - pt_i * g.p);
-            cp_async_16(tile + r * rowlen + v * 4, vb + ((long long)d * g.H + y) * g.W + x0 + v * 4);
-            v += dv; r += dr;
-            if (v >= vec_per_row) { v -= vec_per_row; ++r; }
-        }
-    }
+    load_tile_async(tile, vb, g, tp, hp, x0, rows, rowlen);
     cp_async_wait_all();
     __syncthreads();
     // ---- perturbations applied in shared memory (only when requested / when the cube touches this tile)
@@ -137,25 +141,28 @@ patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
         while (r < rows) {
             const int pt_i = r / g.p;
             const int d = tp * g.pt + pt_i, y = hp * g.p + (r - pt_i * g.p);
-            tile[r * rowlen + c] = perturb(tile[r * rowlen + c], d, y, x0 + c, a, has_alpha, oc, oval);
+            tile[r * rowlen + c] = perturb(tile[r * rowlen + c], d, y, x0 + c, a, has_alpha, hit ? oc : nullptr, oval);
             c += dc; r += dr;
             if (c >= rowlen) { c -= rowlen; ++r; }
         }
         __syncthreads();
     }
-    patch_stats(tile, g, rows, rowlen, eps, s_part, s_mean, s_rstd);
-    // ---- normalise + affine, write bf16 rows; consecutive threads write consecutive pairs of a patch row
-    const long long tok0 = (((long long)b * g.T + tp) * g.Hp + hp) * g.Wp + (long long)gw * g.G;
-    PairIter it; it.init(g, rows);
-    while (it.j < g.G) {
-        const int e = it.r * g.p + it.c;
-        const float mean = s_mean[it.j], rstd = s_rstd[it.j];
-        const float2 v = *reinterpret_cast<const float2*>(tile + it.r * rowlen + it.j * g.p + it.c);
-        const float2 gm = *reinterpret_cast<const float2*>(gamma + e);
-        const float2 bt = *reinterpret_cast<const float2*>(beta + e);
-        *reinterpret_cast<uint32_t*>(out + (tok0 + it.j) * g.P + e) =
-            pack_bf16((v.x - mean) * rstd * gm.x + bt.x, (v.y - mean) * rstd * gm.y + bt.y);
-        it.next();
+    QuadMap m; m.init(g, rowlen);
+    patch_stats(tile, g, m, rows, rowlen, eps, s_part, s_mean, s_rstd);
+    // ---- normalise + affine, 4 voxels -> 4 bf16 (8 bytes) per step
+    if (m.active) {
+        const long long tok = (((long long)b * g.T + tp) * g.Hp + hp) * g.Wp + (long long)gw * g.G + m.j;
+        const float mean = s_mean[m.j], rstd = s_rstd[m.j];
+        __nv_bfloat16* orow = out + tok * g.P;
+        for (int r = m.rgi; r < rows; r += m.rgq) {
+            const int e = r * g.p + m.c;
+            const float4 v = *reinterpret_cast<const float4*>(tile + r * rowlen + m.cq * 4);
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + e);
+            const float4 bt = *reinterpret_cast<const float4*>(beta + e);
+            *reinterpret_cast<uint2*>(orow + e) =
+                make_uint2(pack_bf16((v.x - mean) * rstd * gm.x + bt.x, (v.y - mean) * rstd * gm.y + bt.y),
+                           pack_bf16((v.z - mean) * rstd * gm.z + bt.z, (v.w - mean) * rstd * gm.w + bt.w));
+        }
     }
 }
 
@@ -180,19 +187,10 @@ patchify_ln_bwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
     const bool has_alpha = alpha != nullptr;
     const float a = has_alpha ? alpha[b] : 1.f;
     const int x0 = gw * rowlen;
-    const int vec_per_row = rowlen >> 2;
     const long long tok0 = (((long long)b * g.T + tp) * g.Hp + hp) * g.Wp + (long long)gw * g.G;
     __nv_bfloat16* dys = reinterpret_cast<__nv_bfloat16*>(tile + rows * rowlen);   // [G][P] bf16 (contiguous in global)
+    load_tile_async(tile, vb, g, tp, hp, x0, rows, rowlen);
     {
-        int r = threadIdx.x / vec_per_row, v = threadIdx.x % vec_per_row;
-        const int dr = blockDim.x / vec_per_row, dv = blockDim.x % vec_per_row;
-        while (r < rows) {
-            const int pt_i = r / g.p;
-            const int d = tp * g.pt + pt_i, y = hp * g.p + (r - pt_i * g.p);
-            cp_async_16(tile + r * rowlen + v * 4, vb + ((long long)d * g.H + y) * g.W + x0 + v * 4);
-            v += dv; r += dr;
-            if (v >= vec_per_row) { v -= vec_per_row; ++r; }
-        }
         const int n16 = g.G * g.P / 8;                      // the CTA's G patches are adjacent rows of dY
         const __nv_bfloat16* src = dy + tok0 * g.P;
         for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async_16(dys + i * 8, src + i * 8);
@@ -203,35 +201,48 @@ patchify_ln_bwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
         for (int i = threadIdx.x; i < rows * rowlen; i += blockDim.x) tile[i] = 1.f + a * (tile[i] - 1.f);
         __syncthreads();
     }
-    patch_stats(tile, g, rows, rowlen, eps, s_part, s_mean, s_rstd);
+    QuadMap m; m.init(g, rowlen);
+    patch_stats(tile, g, m, rows, rowlen, eps, s_part, s_mean, s_rstd);
     // ---- per-patch sum(g) and sum(g * xhat), g = dY * gamma (dY tile is in shared memory)
-    patch_reduce2(g, rows, rowlen, s_part, s_mg, s_mgx, [&](int r, int col) {
-        const int j = col / g.p, e = r * g.p + (col - j * g.p);
-        const float gg = __bfloat162float(dys[j * g.P + e]) * gamma[e];
-        return make_float2(gg, gg * (tile[r * rowlen + col] - s_mean[j]) * s_rstd[j]);
-    });
+    float sg = 0.f, sgx = 0.f;
+    if (m.active) {
+        const float mean = s_mean[m.j], rstd = s_rstd[m.j];
+        for (int r = m.rgi; r < rows; r += m.rgq) {
+            const int e = r * g.p + m.c;
+            const float4 v = *reinterpret_cast<const float4*>(tile + r * rowlen + m.cq * 4);
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + e);
+            const uint2 dd = *reinterpret_cast<const uint2*>(dys + m.j * g.P + e);
+            const float2 d01 = unpack_bf16(dd.x), d23 = unpack_bf16(dd.y);
+            const float g0 = d01.x * gm.x, g1 = d01.y * gm.y, g2 = d23.x * gm.z, g3 = d23.y * gm.w;
+            sg += (g0 + g1) + (g2 + g3);
+            sgx += (g0 * (v.x - mean) + g1 * (v.y - mean) + g2 * (v.z - mean) + g3 * (v.w - mean)) * rstd;
+        }
+    }
+    patch_reduce2(g, m, sg, sgx, s_part, s_mg, s_mgx);
     // ---- dx in place of x (same tile positions), then store coalesced along W
-    {
-        PairIter it; it.init(g, rows);
+    if (m.active) {
+        const float mean = s_mean[m.j], rstd = s_rstd[m.j];
         const float invP = 1.f / g.P;
-        while (it.j < g.G) {
-            const int e = it.r * g.p + it.c;
-            const float mean = s_mean[it.j], rstd = s_rstd[it.j];
-            const float mg = s_mg[it.j] * invP, mgx = s_mgx[it.j] * invP;
-            float2* tp2 = reinterpret_cast<float2*>(tile + it.r * rowlen + it.j * g.p + it.c);
-            const float2 v = *tp2;
-            const float2 gm = *reinterpret_cast<const float2*>(gamma + e);
-            const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(dys + it.j * g.P + e));
-            float2 o;
-            o.x = rstd * (d.x * gm.x - mg - (v.x - mean) * rstd * mgx);
-            o.y = rstd * (d.y * gm.y - mg - (v.y - mean) * rstd * mgx);
-            *tp2 = o;
-            it.next();
+        const float mg = s_mg[m.j] * invP, mgx = s_mgx[m.j] * invP;
+        for (int r = m.rgi; r < rows; r += m.rgq) {
+            const int e = r * g.p + m.c;
+            float4* tp4 = reinterpret_cast<float4*>(tile + r * rowlen + m.cq * 4);
+            const float4 v = *tp4;
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + e);
+            const uint2 dd = *reinterpret_cast<const uint2*>(dys + m.j * g.P + e);
+            const float2 d01 = unpack_bf16(dd.x), d23 = unpack_bf16(dd.y);
+            float4 o;
+            o.x = rstd * (d01.x * gm.x - mg - (v.x - mean) * rstd * mgx);
+            o.y = rstd * (d01.y * gm.y - mg - (v.y - mean) * rstd * mgx);
+            o.z = rstd * (d23.x * gm.z - mg - (v.z - mean) * rstd * mgx);
+            o.w = rstd * (d23.y * gm.w - mg - (v.w - mean) * rstd * mgx);
+            *tp4 = o;
         }
     }
     __syncthreads();
     float* gb = grad + (sum_over_batch ? 0 : (long long)b * g.D * g.H * g.W);
     {
+        const int vec_per_row = rowlen >> 2;
         int r = threadIdx.x / vec_per_row, v = threadIdx.x % vec_per_row;
         const int dr = blockDim.x / vec_per_row, dv = blockDim.x % vec_per_row;
         while (r < rows) {
@@ -261,7 +272,7 @@ static int make_geom(PatchGeom& g, long long vol_stride, int B, int D, int H, in
     // patches per CTA: largest divisor of Wp with tile <= 96 KB and <= 32 patches
     int G = 1;
     for (int c = 1; c <= g.Wp && c <= 32; ++c)
-        if (g.Wp % c == 0 && (long long)c * g.P * bytes_per_elem <= 100 * 1024 && c * p <= 256) G = c;
+        if (g.Wp % c == 0 && (long long)c * g.P * bytes_per_elem <= 100 * 1024 && c * p <= 1024) G = c;
     g.G = G;
     CTC_REQUIRE((long long)G * g.P * bytes_per_elem <= 200 * 1024, "patchify: patch of %d voxels does not fit shared memory", g.P);
     CTC_REQUIRE(g.P % 8 == 0, "patchify: patch volume %d must be a multiple of 8", g.P);

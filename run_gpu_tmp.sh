@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python tools/prof_step.py 8 > gpurun_out/r6_plain.log 2>&1 &&
-timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
-   -k regex:"peg_kernel|patchify_ln_bwd|patchify_ln_fwd|attn_bwd_dkv_kernel<96|attn_fwd_kernel<192|gemm_tcgen05_kernel<256, 1>" \
-   -c 14 -o gpurun_out/r6_prof python tools/prof_step.py 8 > gpurun_out/r6_ncu.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_ops.py -q -m gpu 2>&1 | grep -v Warning | tail -n 12 > gpurun_out/r7_ops.log
+timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_attribution.py -q -m gpu -s 2>&1 | grep -v Warning | tail -n 60 > gpurun_out/r7_model.log
+timeout 600 python tools/time_engine.py 8 > gpurun_out/r7_time_b8.log 2>&1
 echo done
