@@ -34,9 +34,9 @@ extern "C" int ctc_device_check(void) {
 }
 
 extern "C" int ctc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldc, int M,
-                             int N, int K, int epi, const float* bias, const float* resid, int64_t ldr, int impl,
-                             void* stream) {
-    CTC_REQUIRE(epi == CTC_EPI_BF16 || epi == CTC_EPI_F32, "ctc_gemm_bf16: epilogue %d not available through this entry", epi);
-    return gemm_bf16(A, lda, B, ldb, out, ldc, M, N, K, epi, bias, resid, ldr, nullptr, nullptr, impl,
+                             int N, int K, int epi, const float* bias, const float* resid, int64_t ldr, void* aux,
+                             int64_t ldaux, int impl, void* stream) {
+    CTC_REQUIRE(epi != CTC_EPI_ARGMAX, "ctc_gemm_bf16: the arg-max epilogue is reached through ctc_vq_argmax");
+    return gemm_bf16(A, lda, B, ldb, out, ldc, M, N, K, epi, bias, resid, ldr, aux, ldaux, nullptr, nullptr, impl,
                      (cudaStream_t)stream);
 }

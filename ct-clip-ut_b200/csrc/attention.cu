@@ -44,6 +44,13 @@ struct AttnParams {
     float* delta;                                        // [R, heads]
 };
 
+// MUFU.EX2 directly (fast_exp2() without fast-math adds denormal range handling around it)
+CTC_DEVINL float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 CTC_DEVINL long long seq_row(const AttnParams& p, int s, int i) {
     if (p.mode == CTC_MODE_SPATIAL) return (long long)s * p.HW + i;
     const int b = s / p.HW, hw = s % p.HW;
@@ -226,13 +233,13 @@ attn_fwd_kernel(const AttnParams p) {
                 const int j = kb * KBLK + nt * 8 + 2 * t;
                 if (i0 < p.n) {
                     float* pr = p.probs + (((long long)s * p.heads + head) * p.n + i0) * p.n + j;
-                    if (j < p.n) pr[0] = exp2f(sc[nt][0] - lse2_0);
-                    if (j + 1 < p.n) pr[1] = exp2f(sc[nt][1] - lse2_0);
+                    if (j < p.n) pr[0] = fast_exp2(sc[nt][0] - lse2_0);
+                    if (j + 1 < p.n) pr[1] = fast_exp2(sc[nt][1] - lse2_0);
                 }
                 if (i1 < p.n) {
                     float* pr = p.probs + (((long long)s * p.heads + head) * p.n + i1) * p.n + j;
-                    if (j < p.n) pr[0] = exp2f(sc[nt][2] - lse2_1);
-                    if (j + 1 < p.n) pr[1] = exp2f(sc[nt][3] - lse2_1);
+                    if (j < p.n) pr[0] = fast_exp2(sc[nt][2] - lse2_1);
+                    if (j + 1 < p.n) pr[1] = fast_exp2(sc[nt][3] - lse2_1);
                 }
             }
             continue;
@@ -247,13 +254,13 @@ attn_fwd_kernel(const AttnParams p) {
         bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
         bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
         const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
-        const float c0 = exp2f(m0 - nm0), c1 = exp2f(m1 - nm1);
+        const float c0 = fast_exp2(m0 - nm0), c1 = fast_exp2(m1 - nm1);
         m0 = nm0; m1 = nm1;
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int nt = 0; nt < KBLK / 8; ++nt) {
-            sc[nt][0] = exp2f(sc[nt][0] - m0); sc[nt][1] = exp2f(sc[nt][1] - m0);
-            sc[nt][2] = exp2f(sc[nt][2] - m1); sc[nt][3] = exp2f(sc[nt][3] - m1);
+            sc[nt][0] = fast_exp2(sc[nt][0] - m0); sc[nt][1] = fast_exp2(sc[nt][1] - m0);
+            sc[nt][2] = fast_exp2(sc[nt][2] - m1); sc[nt][3] = fast_exp2(sc[nt][3] - m1);
             rs0 += sc[nt][0] + sc[nt][1]; rs1 += sc[nt][2] + sc[nt][3];
         }
         l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
@@ -398,8 +405,8 @@ attn_bwd_dq_kernel(const AttnParams p) {
         for (int nt = 0; nt < KBLK / 8; ++nt) {
             float dp[4] = {0.f, 0.f, 0.f, 0.f};
             mma_rowsB(dp, ado, vs_a, kb * KBLK + nt * 8, lane);
-            float p0 = exp2f(sc[nt][0] - lse2_0), p1 = exp2f(sc[nt][1] - lse2_0);
-            float p2 = exp2f(sc[nt][2] - lse2_1), p3 = exp2f(sc[nt][3] - lse2_1);
+            float p0 = fast_exp2(sc[nt][0] - lse2_0), p1 = fast_exp2(sc[nt][1] - lse2_0);
+            float p2 = fast_exp2(sc[nt][2] - lse2_1), p3 = fast_exp2(sc[nt][3] - lse2_1);
             if (need_mask) {
                 const int j = kb * KBLK + nt * 8 + 2 * t;
                 if (j >= p.n) { p0 = 0.f; p2 = 0.f; }
@@ -517,8 +524,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
                 st[2] += bias[b0 - tab1]; st[3] += bias[b1 - tab1];
             }
             const float l0 = lse2h[i], l1 = lse2h[i + 1];      // +inf for padded queries -> P = 0
-            pt[nt][0] = exp2f(st[0] - l0); pt[nt][1] = exp2f(st[1] - l1);
-            pt[nt][2] = exp2f(st[2] - l0); pt[nt][3] = exp2f(st[3] - l1);
+            pt[nt][0] = fast_exp2(st[0] - l0); pt[nt][1] = fast_exp2(st[1] - l1);
+            pt[nt][2] = fast_exp2(st[2] - l0); pt[nt][3] = fast_exp2(st[3] - l1);
             float dp[4] = {0.f, 0.f, 0.f, 0.f};
             mma_rowsB(dp, av, dos_a, qblk * KBLK + nt * 8, lane);
             const float dd0 = dlh[i], dd1 = dlh[i + 1];

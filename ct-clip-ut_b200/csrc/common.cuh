@@ -59,11 +59,28 @@ CTC_DEVINL float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-CTC_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (F.gelu default, attention.py:41) and its derivative from ONE exponential:
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z)   (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7)
+// with z = |x|/sqrt(2), so exp(-z^2) = exp(-x^2/2) is also the Gaussian density the derivative needs.
+CTC_DEVINL void gelu_parts(float x, float& cdf, float& pdf) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    const float e = __expf(-z * z);
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
+                                0.254829592f);
+    const float erf_abs = fmaf(-poly, e, 1.0f);
+    cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+    pdf = 0.3989422804014327f * e;
+}
+CTC_DEVINL float gelu_erf(float x) {
+    float cdf, pdf;
+    gelu_parts(x, cdf, pdf);
+    return x * cdf;
+}
 CTC_DEVINL float gelu_erf_grad(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    float cdf, pdf;
+    gelu_parts(x, cdf, pdf);
+    return fmaf(x, pdf, cdf);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -227,8 +227,10 @@ geglu_fwd_kernel(const __nv_bfloat16* __restrict__ u, long long R, int F, __nv_b
     if (idx >= R * f8) return;
     const long long r = idx / f8;
     const int f = (int)(idx % f8) * 8;
-    const uint4 xa = *reinterpret_cast<const uint4*>(u + r * 2 * F + f);
-    const uint4 ga = *reinterpret_cast<const uint4*>(u + r * 2 * F + F + f);
+    // grouped layout: value column f lives at 64*(f/32) + f%32, its gate 32 columns further
+    const long long uo = r * 2 * F + 64 * (f / 32) + (f % 32);
+    const uint4 xa = *reinterpret_cast<const uint4*>(u + uo);
+    const uint4 ga = *reinterpret_cast<const uint4*>(u + uo + 32);
     const uint32_t xs[4] = {xa.x, xa.y, xa.z, xa.w}, gs[4] = {ga.x, ga.y, ga.z, ga.w};
     uint32_t o[4];
 #pragma unroll
@@ -247,8 +249,9 @@ geglu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
     if (idx >= R * f8) return;
     const long long r = idx / f8;
     const int f = (int)(idx % f8) * 8;
-    const uint4 xa = *reinterpret_cast<const uint4*>(u + r * 2 * F + f);
-    const uint4 ga = *reinterpret_cast<const uint4*>(u + r * 2 * F + F + f);
+    const long long uo = r * 2 * F + 64 * (f / 32) + (f % 32);
+    const uint4 xa = *reinterpret_cast<const uint4*>(u + uo);
+    const uint4 ga = *reinterpret_cast<const uint4*>(u + uo + 32);
     const uint4 da = *reinterpret_cast<const uint4*>(dh + r * F + f);
     const uint32_t xs[4] = {xa.x, xa.y, xa.z, xa.w}, gs[4] = {ga.x, ga.y, ga.z, ga.w}, ds[4] = {da.x, da.y, da.z, da.w};
     uint32_t ox[4], og[4];
@@ -258,8 +261,8 @@ geglu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
         ox[i] = pack_bf16(gelu_erf(gv.x) * dv.x, gelu_erf(gv.y) * dv.y);
         og[i] = pack_bf16(xv.x * gelu_erf_grad(gv.x) * dv.x, xv.y * gelu_erf_grad(gv.y) * dv.y);
     }
-    *reinterpret_cast<uint4*>(du + r * 2 * F + f) = make_uint4(ox[0], ox[1], ox[2], ox[3]);
-    *reinterpret_cast<uint4*>(du + r * 2 * F + F + f) = make_uint4(og[0], og[1], og[2], og[3]);
+    *reinterpret_cast<uint4*>(du + uo) = make_uint4(ox[0], ox[1], ox[2], ox[3]);
+    *reinterpret_cast<uint4*>(du + uo + 32) = make_uint4(og[0], og[1], og[2], og[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -344,7 +347,7 @@ extern "C" int ctc_peg(const float* x, int B, int T, int H, int W, int C, const 
 }
 
 extern "C" int ctc_geglu_fwd(const void* u, int R, int F, void* h, void* stream) {
-    CTC_REQUIRE(F % 8 == 0, "geglu: F=%d must be a multiple of 8", F);
+    CTC_REQUIRE(F % 32 == 0, "geglu: F=%d must be a multiple of 32 (grouped [32 value | 32 gate] layout)", F);
     const long long total = (long long)R * (F / 8);
     geglu_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)u, R, F, (__nv_bfloat16*)h);
@@ -353,7 +356,7 @@ extern "C" int ctc_geglu_fwd(const void* u, int R, int F, void* h, void* stream)
 }
 
 extern "C" int ctc_geglu_bwd(const void* u, const void* dh, int R, int F, void* du, void* stream) {
-    CTC_REQUIRE(F % 8 == 0, "geglu: F=%d must be a multiple of 8", F);
+    CTC_REQUIRE(F % 32 == 0, "geglu: F=%d must be a multiple of 32 (grouped [32 value | 32 gate] layout)", F);
     const long long total = (long long)R * (F / 8);
     geglu_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)u, (const __nv_bfloat16*)dh, R, F, (__nv_bfloat16*)du);

@@ -29,6 +29,8 @@ struct GemmArgs {
     const float* bias;  // [N] or null
     const float* resid; // fp32 [M, ldr] or null (may alias out)
     long long ldr;
+    void* aux;          // EPI_GEGLU: optional u bf16 [M, N] out; EPI_GEGLU_BWD: u bf16 [M, 2N] in
+    long long ldaux;
     float* top2_val;    // EPI_ARGMAX: [M, n_tiles*2]
     int* top2_idx;
     int n_tiles_n;
@@ -146,9 +148,10 @@ CTC_DEVINL void prefetch_resid(const GemmArgs& g, int row0, int col0, int lane, 
                              : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-// bf16 chunk: 32 rows x 64 columns (acc already packed to 32 x bf16x2)
+// bf16 chunk: 32 rows x 64 columns (acc already packed to 32 x bf16x2) -> dst[row, col0 .. col0+64)
 CTC_DEVINL void epilogue_bf16_staged(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
-                                     const uint32_t (&pk)[32]) {
+                                     const uint32_t (&pk)[32], __nv_bfloat16* dst = nullptr, long long ld = 0) {
+    if (!dst) { dst = reinterpret_cast<__nv_bfloat16*>(g.out); ld = g.ldc; }
 #pragma unroll
     for (int u = 0; u < 8; ++u)
         *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
@@ -160,8 +163,39 @@ CTC_DEVINL void epilogue_bf16_staged(const GemmArgs& g, uint8_t* stage, int row0
         const int rl = (lane >> 3) + 4 * i;
         const int row = row0 + rl;
         const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(rl, u));
-        if (row < g.M)
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + (long long)row * g.ldc + col0 + u * 8) = v;
+        if (row < g.M) *reinterpret_cast<uint4*>(dst + (long long)row * ld + col0 + u * 8) = v;
+    }
+    __syncwarp();
+}
+// bf16 half chunk: 32 rows x 32 columns (16 x bf16x2 per thread) -> dst[row, col0 .. col0+32); 8 rows x 64 B per access
+CTC_DEVINL void epilogue_bf16_staged32(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
+                                       const uint32_t (&pk)[16], __nv_bfloat16* dst, long long ld) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
+            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    __syncwarp();
+    const int u = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rl = (lane >> 2) + 8 * i;
+        const int row = row0 + rl;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(rl, u));
+        if (row < g.M) *reinterpret_cast<uint4*>(dst + (long long)row * ld + col0 + u * 8) = v;
+    }
+    __syncwarp();
+}
+// coalesced load of a 32-row x 128-byte chunk (src[row, col0 .. col0+64) bf16) into the swizzled staging tile
+CTC_DEVINL void stage_load_bf16_64(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
+                                   const __nv_bfloat16* src, long long ld) {
+    const int u = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = (lane >> 3) + 4 * i;
+        const int row = row0 + rl;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < g.M) v = *reinterpret_cast<const uint4*>(src + (long long)row * ld + col0 + u * 8);
+        *reinterpret_cast<uint4*>(stage + stage_off(rl, u)) = v;
     }
     __syncwarp();
 }
@@ -297,6 +331,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const long long o = ((long long)row * g.n_tiles_n + tn) * 2;
                     g.top2_val[o] = t2[0].v0; g.top2_val[o + 1] = t2[0].v1;
                     g.top2_idx[o] = t2[0].i0; g.top2_idx[o + 1] = t2[0].i1;
+                }
+            } else if constexpr (EPI == CTC_EPI_GEGLU) {
+                // columns come in 64-wide groups [32 value | 32 gate] (weights interleaved at plan time):
+                // h = gelu(gate) * value (attention.py:38-41) straight from the fp32 accumulators
+                __nv_bfloat16* hout = reinterpret_cast<__nv_bfloat16*>(g.out);
+                __nv_bfloat16* uout = reinterpret_cast<__nv_bfloat16*>(g.aux);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 64) {
+                    const int col0 = tn * BN + c;
+                    if (col0 >= g.N) break;
+                    uint32_t xv[32], gv[32];
+                    tmem_ld_32x32b_x32(taddr + c, xv);
+                    tmem_ld_32x32b_x32(taddr + c + 32, gv);
+                    tmem_ld_wait();
+                    if (uout) {
+                        uint32_t pk[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            pk[j] = pack_bf16(__uint_as_float(xv[2 * j]), __uint_as_float(xv[2 * j + 1]));
+                            pk[16 + j] = pack_bf16(__uint_as_float(gv[2 * j]), __uint_as_float(gv[2 * j + 1]));
+                        }
+                        epilogue_bf16_staged(g, stage, row0, col0, lane, pk, uout, g.ldaux);
+                    }
+                    uint32_t hk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        hk[j] = pack_bf16(gelu_erf(__uint_as_float(gv[2 * j])) * __uint_as_float(xv[2 * j]),
+                                          gelu_erf(__uint_as_float(gv[2 * j + 1])) * __uint_as_float(xv[2 * j + 1]));
+                    epilogue_bf16_staged32(g, stage, row0, col0 / 2, lane, hk, hout, g.ldc);
+                }
+            } else if constexpr (EPI == CTC_EPI_GEGLU_BWD) {
+                // acc = dh chunk (32 columns); u = [value | gate] of the same columns is one 128-byte row segment:
+                // du_value = gelu(gate) * dh, du_gate = value * gelu'(gate) * dh, written back in the same layout
+                const __nv_bfloat16* uin = reinterpret_cast<const __nv_bfloat16*>(g.aux);
+                __nv_bfloat16* duout = reinterpret_cast<__nv_bfloat16*>(g.out);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    const int col0 = tn * BN + c;
+                    if (col0 >= g.N) break;
+                    stage_load_bf16_64(g, stage, row0, 2 * col0, lane, uin, g.ldaux);
+                    uint32_t dh[32];
+                    tmem_ld_32x32b_x32(taddr + c, dh);
+                    tmem_ld_wait();
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint4 xa = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u));
+                        const uint4 ga = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u + 4));
+                        const uint32_t xs[4] = {xa.x, xa.y, xa.z, xa.w}, gs[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 xf = unpack_bf16(xs[e]), gf = unpack_bf16(gs[e]);
+                            const float d0 = __uint_as_float(dh[u * 8 + 2 * e]), d1 = __uint_as_float(dh[u * 8 + 2 * e + 1]);
+                            pk[u * 4 + e] = pack_bf16(gelu_erf(gf.x) * d0, gelu_erf(gf.y) * d1);
+                            pk[16 + u * 4 + e] = pack_bf16(xf.x * gelu_erf_grad(gf.x) * d0, xf.y * gelu_erf_grad(gf.y) * d1);
+                        }
+                    }
+                    __syncwarp();
+                    epilogue_bf16_staged(g, stage, row0, 2 * col0, lane, pk, duout, g.ldc);
                 }
             } else if constexpr (EPI == CTC_EPI_F32) {
                 const bool aligned = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0) &&
@@ -453,14 +546,21 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArg
 }
 
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldc, int M, int N,
-              int K, int epi, const float* bias, const float* resid, long long ldr, float* top2_val, int* top2_idx,
-              int impl, cudaStream_t st) {
+              int K, int epi, const float* bias, const float* resid, long long ldr, void* aux, long long ldaux,
+              float* top2_val, int* top2_idx, int impl, cudaStream_t st) {
     CTC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.out = out; g.ldc = ldc; g.bias = bias; g.resid = resid; g.ldr = ldr;
-    g.top2_val = top2_val; g.top2_idx = top2_idx;
+    g.top2_val = top2_val; g.top2_idx = top2_idx; g.aux = aux; g.ldaux = ldaux;
+    if (epi == CTC_EPI_GEGLU || epi == CTC_EPI_GEGLU_BWD) {
+        CTC_REQUIRE(impl == CTC_GEMM_TCGEN05, "gemm: the fused GEGLU epilogues exist only in the tcgen05 kernel");
+        CTC_REQUIRE(N % 64 == 0 && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                    (!aux || (ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0)),
+                    "gemm: GEGLU epilogues need N %% 64 == 0 and 16-byte aligned bf16 rows (N=%d)", N);
+        CTC_REQUIRE(epi != CTC_EPI_GEGLU_BWD || aux, "gemm: GEGLU backward epilogue needs the saved pre-activation u");
+    }
     if (impl == CTC_GEMM_SIMT) {
-        CTC_REQUIRE(epi != CTC_EPI_ARGMAX, "gemm: SIMT comparator has no arg-max epilogue");
+        CTC_REQUIRE(epi == CTC_EPI_BF16 || epi == CTC_EPI_F32, "gemm: SIMT comparator has only the plain epilogues");
         dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
         if (epi == CTC_EPI_BF16)
             gemm_simt_kernel<CTC_EPI_BF16><<<grid, block, 0, st>>>((const __nv_bfloat16*)A, lda,
@@ -483,6 +583,10 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
             return bn256 ? launch_tc<256, CTC_EPI_BF16>(ta, tb, g, st) : launch_tc<128, CTC_EPI_BF16>(ta, tb, g, st);
         case CTC_EPI_F32:
             return bn256 ? launch_tc<256, CTC_EPI_F32>(ta, tb, g, st) : launch_tc<128, CTC_EPI_F32>(ta, tb, g, st);
+        case CTC_EPI_GEGLU:
+            return bn256 ? launch_tc<256, CTC_EPI_GEGLU>(ta, tb, g, st) : launch_tc<128, CTC_EPI_GEGLU>(ta, tb, g, st);
+        case CTC_EPI_GEGLU_BWD:
+            return bn256 ? launch_tc<256, CTC_EPI_GEGLU_BWD>(ta, tb, g, st) : launch_tc<128, CTC_EPI_GEGLU_BWD>(ta, tb, g, st);
         case CTC_EPI_ARGMAX:
             CTC_REQUIRE(top2_val && top2_idx, "gemm: arg-max epilogue needs top2 buffers");
             return launch_tc<256, CTC_EPI_ARGMAX>(ta, tb, g, st);

@@ -328,7 +328,7 @@ extern "C" int ctc_vq_argmax(const float* x, const void* x_bf16, int R, int C, c
                              void* stream) {
     CTC_REQUIRE(C % 4 == 0, "vq: C=%d must be a multiple of 4", C);
     const int n_tiles = gemm_argmax_tiles(K);
-    if (int e = gemm_bf16(x_bf16, C, codebook_bf16, C, nullptr, 0, R, K, C, CTC_EPI_ARGMAX, nullptr, nullptr, 0,
+    if (int e = gemm_bf16(x_bf16, C, codebook_bf16, C, nullptr, 0, R, K, C, CTC_EPI_ARGMAX, nullptr, nullptr, 0, nullptr, 0,
                           cand_val, cand_idx, CTC_GEMM_TCGEN05, (cudaStream_t)stream))
         return e;
     vq_refine_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, R, C, codebook, cand_val, cand_idx,

@@ -21,7 +21,7 @@ P, I, L, F = c_void_p, c_int, c_int64, c_float
 # name -> argument ctypes (all functions return int status, except the two noted below)
 SIGNATURES = {
     "ctc_device_check": [],
-    "ctc_gemm_bf16": [P, L, P, L, P, L, I, I, I, I, P, P, L, I, P],
+    "ctc_gemm_bf16": [P, L, P, L, P, L, I, I, I, I, P, P, L, P, L, I, P],
     "ctc_patchify_ln_fwd": [P, L, I, I, I, I, I, I, P, P, F, P, P, F, P, P],
     "ctc_patchify_ln_bwd": [P, L, I, I, I, I, I, I, P, F, P, P, P, I, F, P],
     "ctc_layernorm_fwd": [P, I, I, P, P, F, P, P, P, P],
@@ -57,7 +57,7 @@ SIGNATURES = {
 OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, []),
                  "ctc_launch_count": (ctypes.c_longlong, [])}
 
-EPI_BF16, EPI_F32, EPI_ARGMAX = 0, 1, 2
+EPI_BF16, EPI_F32, EPI_ARGMAX, EPI_GEGLU, EPI_GEGLU_BWD = 0, 1, 2, 3, 4
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
 MODE_SPATIAL, MODE_TEMPORAL = 0, 1
 

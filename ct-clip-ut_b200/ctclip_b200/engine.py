@@ -68,18 +68,20 @@ class Engine:
         self.cfg = plan.cfg
         self.dev = plan.device
         self.gemm_impl = gemm_impl
+        self.fuse_geglu_bwd = False
 
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
-    def gemm(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, epi: int, bias=None, resid=None):
-        """out[M,N] = a[M,K] @ w[N,K]^T (+bias)(+resid)"""
+    def gemm(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, epi: int, bias=None, resid=None, aux=None):
+        """out = a[M,K] @ w[N,K]^T with the epilogue `epi` (+bias)(+resid); `aux`: GEGLU pre-activation buffer"""
         M, K = a.shape
         N = w.shape[0]
-        assert w.shape[1] == K and out.shape[0] == M and out.shape[1] == N
+        assert w.shape[1] == K and out.shape[0] == M
         call("ctc_gemm_bf16", a, a.stride(0), w, w.stride(0), out, out.stride(0), M, N, K, epi, bias, resid,
-             resid.stride(0) if resid is not None else 0, self.gemm_impl, stream_ptr())
+             resid.stride(0) if resid is not None else 0, aux, aux.stride(0) if aux is not None else 0,
+             self.gemm_impl, stream_ptr())
         return out
 
     def layernorm(self, x, g, b, y_bf16=None, y_f32=None, xraw=None):
@@ -123,9 +125,15 @@ class Engine:
         # x = ff(x) + x                                                    attention.py:43-51, 334
         xn2 = xn  # reuse
         self.layernorm(x2, lw.ff_ln_w, lw.ff_ln_b, y_bf16=xn2)
-        u = self.gemm(xn2, lw.w1, self._empty(R, 2 * FP, dtype=bf), EPI_BF16)
+        # Linear(dim, 2*inner) + GEGLU fused in the GEMM epilogue; the pre-activation u is only written when
+        # the backward pass will need it
+        u = self._empty(R, 2 * FP, dtype=bf) if save else None
         hff = self._empty(R, FP, dtype=bf)
-        call("ctc_geglu_fwd", u, R, FP, hff, stream_ptr())
+        if self.gemm_impl == _lib.GEMM_TCGEN05:
+            self.gemm(xn2, lw.w1, hff, _lib.EPI_GEGLU, aux=u)
+        else:   # SIMT comparator path (tests): plain GEMM + stand-alone GEGLU
+            u = self.gemm(xn2, lw.w1, self._empty(R, 2 * FP, dtype=bf), EPI_BF16)
+            call("ctc_geglu_fwd", u, R, FP, hff, stream_ptr())
         x3 = self.gemm(hff, lw.w2, self._empty(R, C), EPI_F32, resid=x2)
         if save:
             lc.x1, lc.x2, lc.q, lc.kv, lc.o, lc.lse, lc.u = x1, x2, q, kv, o, lse, u
@@ -222,10 +230,16 @@ class Engine:
         if capture is not None:
             capture[tag + "_ff"] = dx3.clone()          # d/d(ff output)  == grad of x3
         # ---- FeedForward
-        dh = self.gemm(dx3_bf, lw.w2_t, self._empty(R, FP, dtype=bf), EPI_BF16)
+        # dh = dx3 @ W2, then the GEGLU adjoint as its own HBM-bound pass.  (A fused GEMM epilogue exists,
+        # EPI_GEGLU_BWD, but four epilogue warps evaluating gelu/gelu' per element made the GEMM 3.6x slower
+        # than GEMM + stand-alone pass on B200 - profiles/r01_geglu_fusion.md - so it is not used.)
         du = self._empty(R, 2 * FP, dtype=bf)
-        call("ctc_geglu_bwd", lc.u, dh, R, FP, du, stream_ptr())
-        del dh
+        if self.fuse_geglu_bwd and self.gemm_impl == _lib.GEMM_TCGEN05:
+            self.gemm(dx3_bf, lw.w2_t, du, _lib.EPI_GEGLU_BWD, aux=lc.u)
+        else:
+            dh = self.gemm(dx3_bf, lw.w2_t, self._empty(R, FP, dtype=bf), EPI_BF16)
+            call("ctc_geglu_bwd", lc.u, dh, R, FP, du, stream_ptr())
+            del dh
         dxn2 = self.gemm(du, lw.w1_t, self._empty(R, C), EPI_F32)
         del du
         dx2, dx2_bf = dx3, dx3_bf

@@ -124,9 +124,12 @@ class Plan:
         lw.wq_t, lw.wkv_t, lw.wout_t = _bf16(wq.t()), _bf16(wkv.t()), _bf16(wout.t())
         lw.ff_ln_w, lw.ff_ln_b = f32("3.0.weight"), f32("3.0.bias")
         w1, w2 = f32("3.1.weight"), f32("3.4.weight")                          # [2F, C], [C, F]
-        w1p = torch.zeros(2 * FP, C, device=w1.device)
-        w1p[:F] = w1[:F]                 # GEGLU value half  (attention.py:40: x, gate = chunk(2))
-        w1p[FP:FP + F] = w1[F:]          # GEGLU gate half
+        # GEGLU halves (attention.py:40: x, gate = chunk(2)), zero-padded to FP and interleaved in 64-row groups
+        # [32 value rows | 32 gate rows] so that a GEMM epilogue thread holds value_j and gate_j of the same j
+        val = torch.zeros(FP, C, device=w1.device)
+        gate = torch.zeros(FP, C, device=w1.device)
+        val[:F], gate[:F] = w1[:F], w1[F:]
+        w1p = torch.stack([val.view(FP // 32, 32, C), gate.view(FP // 32, 32, C)], dim=1).reshape(2 * FP, C)
         w2p = torch.zeros(C, FP, device=w2.device)
         w2p[:, :F] = w2
         lw.w1, lw.w2 = _bf16(w1p), _bf16(w2p)

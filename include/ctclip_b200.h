@@ -29,7 +29,7 @@ extern "C" {
 #define CTC_VERSION 100
 
 /* GEMM epilogues */
-enum { CTC_EPI_BF16 = 0, CTC_EPI_F32 = 1, CTC_EPI_ARGMAX = 2 };
+enum { CTC_EPI_BF16 = 0, CTC_EPI_F32 = 1, CTC_EPI_ARGMAX = 2, CTC_EPI_GEGLU = 3, CTC_EPI_GEGLU_BWD = 4 };
 /* GEMM implementation: tcgen05 is the product path; SIMT is a test comparator */
 enum { CTC_GEMM_TCGEN05 = 0, CTC_GEMM_SIMT = 1 };
 /* sequence mode of the factorised transformer (ctvit.py:94-101) */
@@ -44,9 +44,14 @@ long long ctc_launch_count(void);
 
 /* C[M,N] = A[M,K] * B[N,K]^T, bf16 operands (row strides lda/ldb elements), fp32 accumulate.
  * epi BF16: out bf16 [M,ldc]; F32: out fp32 = acc (+bias[N]) (+resid fp32 [M,ldr], may alias out).
+ * epi GEGLU (FeedForward, attention.py:38-49): the N output columns are 64-wide groups [32 value | 32 gate]
+ *   (weight rows interleaved by the caller); out = gelu(gate)*value bf16 [M, N/2]; aux (optional) receives
+ *   the pre-activation u bf16 [M, N] (stride ldaux) for the backward pass.
+ * epi GEGLU_BWD: acc = dh [M,N]; aux = saved u bf16 [M, 2N]; out = du bf16 [M, 2N] in the same grouped layout.
  * Replaces every nn.Linear / einsum on the path: attention.py:47,49,142,182; ctvit.py:50. */
 int ctc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldc, int M, int N,
-                  int K, int epi, const float* bias, const float* resid, int64_t ldr, int impl, void* stream);
+                  int K, int epi, const float* bias, const float* resid, int64_t ldr, void* aux, int64_t ldaux,
+                  int impl, void* stream);
 
 /* 3-D patchify + LayerNorm(P) (ctvit.py:44-49): volume fp32 [B,1,D,H,W] -> bf16 [B*T*H*W, P]
  * (P = pt*p*p, element order pt,p1,p2).  Fused on load, so perturbed volumes are never
@@ -100,7 +105,9 @@ int ctc_attention_probs(const void* q, int64_t ldq, const void* k, int64_t ldkv,
                         int H, int W, int heads, const float* q_scale, const float* k_scale, float scale,
                         const float* bias_table, int mode, float* probs, void* stream);
 
-/* GEGLU (attention.py:38-41): u bf16 [R, 2*F] (first F columns = x, last F = gate) -> h = gelu(gate)*x bf16 [R,F] */
+/* Stand-alone GEGLU (attention.py:38-41) on the grouped layout of the fused epilogues: u bf16 [R, 2*F] in
+ * 64-wide groups [32 value | 32 gate] -> h = gelu(gate)*value bf16 [R,F]; the product path uses the fused
+ * GEMM epilogues instead, these remain as comparators. */
 int ctc_geglu_fwd(const void* u, int R, int F, void* h, void* stream);
 int ctc_geglu_bwd(const void* u, const void* dh, int R, int F, void* du, void* stream);
 

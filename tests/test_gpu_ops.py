@@ -42,7 +42,7 @@ def test_gemm_bf16_out(lib, impl, M, N, K):
     a = rnd(M, K, seed=1, dtype=torch.bfloat16)
     w = rnd(N, K, seed=2, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
     out = torch.full((M, N), float("nan"), device=dev(), dtype=torch.bfloat16)
-    lib.call("ctc_gemm_bf16", a, K, w, K, out, N, M, N, K, lib.EPI_BF16, None, None, 0, impl, lib.stream_ptr())
+    lib.call("ctc_gemm_bf16", a, K, w, K, out, N, M, N, K, lib.EPI_BF16, None, None, 0, None, 0, impl, lib.stream_ptr())
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t()
     assert torch.isfinite(out.float()).all()
@@ -58,7 +58,7 @@ def test_gemm_f32_bias_resid(lib, impl, M, N, K):
     resid = rnd(M, N, seed=6)
     ref = a.float() @ w.float().t() + bias + resid
     out = resid.clone()   # in-place residual
-    lib.call("ctc_gemm_bf16", a, K, w, K, out, N, M, N, K, lib.EPI_F32, bias, out, N, impl, lib.stream_ptr())
+    lib.call("ctc_gemm_bf16", a, K, w, K, out, N, M, N, K, lib.EPI_F32, bias, out, N, None, 0, impl, lib.stream_ptr())
     torch.cuda.synchronize()
     assert relerr(out, ref) < 2e-5 * math.sqrt(K)
 
@@ -71,7 +71,7 @@ def test_gemm_persistent_many_tiles_repeat(lib):
     outs = []
     for _ in range(2):
         out = torch.empty(M, N, device=dev(), dtype=torch.bfloat16)
-        lib.call("ctc_gemm_bf16", a, K, w, K, out, N, M, N, K, lib.EPI_BF16, None, None, 0, 0, lib.stream_ptr())
+        lib.call("ctc_gemm_bf16", a, K, w, K, out, N, M, N, K, lib.EPI_BF16, None, None, 0, None, 0, 0, lib.stream_ptr())
         outs.append(out)
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1])
@@ -214,19 +214,56 @@ def test_attention_fwd_bwd_probs(lib, mode, B, T, H, W, heads):
 
 
 # --------------------------------------------------------------------------------------- GEGLU
+def _group(x_part, gate_part):
+    """[R,F],[R,F] -> grouped [R, 2F]: 64-wide groups [32 value | 32 gate]"""
+    R, Fp = x_part.shape
+    return torch.stack([x_part.view(R, Fp // 32, 32), gate_part.view(R, Fp // 32, 32)], dim=2).reshape(R, 2 * Fp)
+
+
 def test_geglu_fwd_bwd(lib):
     R, Fp = 333, 256
-    u = rnd(R, 2 * Fp, seed=1, dtype=torch.bfloat16)
+    xp, gp = rnd(R, Fp, seed=1, dtype=torch.bfloat16), rnd(R, Fp, seed=11, dtype=torch.bfloat16)
+    u = _group(xp, gp).contiguous()
     h = torch.empty(R, Fp, device=dev(), dtype=torch.bfloat16)
     lib.call("ctc_geglu_fwd", u, R, Fp, h, lib.stream_ptr())
-    uf = u.float().requires_grad_()
-    ref = F.gelu(uf[:, Fp:]) * uf[:, :Fp]
+    xf, gf = xp.float().requires_grad_(), gp.float().requires_grad_()
+    ref = F.gelu(gf) * xf
     assert relerr(h, ref) < 1e-2
     dh = rnd(R, Fp, seed=2, dtype=torch.bfloat16)
-    (du_ref,) = torch.autograd.grad(ref, uf, dh.float())
+    dx_ref, dg_ref = torch.autograd.grad(ref, [xf, gf], dh.float())
     du = torch.empty(R, 2 * Fp, device=dev(), dtype=torch.bfloat16)
     lib.call("ctc_geglu_bwd", u, dh, R, Fp, du, lib.stream_ptr())
-    assert relerr(du, du_ref) < 1e-2
+    assert relerr(du, _group(dx_ref, dg_ref)) < 1e-2
+
+
+@pytest.mark.parametrize("M,Fp,K", [(300, 256, 64), (13824, 1408, 512), (1000, 128, 512)])
+def test_gemm_fused_geglu_epilogues(lib, M, Fp, K):
+    """Linear + GEGLU (attention.py:47-48) and its adjoint fused into the tcgen05 GEMM epilogues."""
+    a = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    wv = rnd(Fp, K, seed=2, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    wg = rnd(Fp, K, seed=3, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    w = torch.stack([wv.view(Fp // 32, 32, K), wg.view(Fp // 32, 32, K)], dim=1).reshape(2 * Fp, K).contiguous()
+    h = torch.full((M, Fp), float("nan"), device=dev(), dtype=torch.bfloat16)
+    u = torch.full((M, 2 * Fp), float("nan"), device=dev(), dtype=torch.bfloat16)
+    lib.call("ctc_gemm_bf16", a, K, w, K, h, Fp, M, 2 * Fp, K, lib.EPI_GEGLU, None, None, 0, u, 2 * Fp, 0, lib.stream_ptr())
+    xv, xg = a.float() @ wv.float().t(), a.float() @ wg.float().t()
+    assert relerr(u, _group(xv, xg)) < 1e-2
+    assert relerr(h, F.gelu(xg) * xv) < 1e-2
+    h2 = torch.empty_like(h)                                   # without the pre-activation output
+    lib.call("ctc_gemm_bf16", a, K, w, K, h2, Fp, M, 2 * Fp, K, lib.EPI_GEGLU, None, None, 0, None, 0, 0, lib.stream_ptr())
+    assert torch.equal(h, h2)
+    # backward: dh = d @ W2t, du = GEGLU'(u) * dh
+    Kd = 256
+    d = rnd(M, Kd, seed=4, dtype=torch.bfloat16)
+    w2t = rnd(Fp, Kd, seed=5, scale=1 / math.sqrt(Kd), dtype=torch.bfloat16)
+    du = torch.full((M, 2 * Fp), float("nan"), device=dev(), dtype=torch.bfloat16)
+    lib.call("ctc_gemm_bf16", d, Kd, w2t, Kd, du, 2 * Fp, M, Fp, Kd, lib.EPI_GEGLU_BWD, None, None, 0, u, 2 * Fp, 0,
+             lib.stream_ptr())
+    dh = d.float() @ w2t.float().t()
+    uf = u.float().view(M, Fp // 32, 2, 32)
+    xs, gs = uf[:, :, 0].reshape(M, Fp).requires_grad_(), uf[:, :, 1].reshape(M, Fp).requires_grad_()
+    dx_ref, dg_ref = torch.autograd.grad(F.gelu(gs) * xs, [xs, gs], dh)
+    assert relerr(du, _group(dx_ref, dg_ref)) < 1.5e-2
 
 
 # --------------------------------------------------------------------------------------- patchify
