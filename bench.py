@@ -117,6 +117,68 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ------------------------------------------------------------------------------------------ attribution sub-metric
+def occlusion_flops(T=24, HW=576, n_layers=4, nt=2):
+    """(dense-equivalent, executed) FLOPs of one reference-sized occlusion sweep (12 167 windows + baseline),
+    SURVEY §8d.  Executed = dense minus the patch embedding of the windows and minus the spatial-transformer
+    frames the cube cannot reach (Engine.forward_occluded)."""
+    lin_tok = 2 * 512 * (256 + 512 + 256 + 2730 + 1365)
+    peg_tok = 2 * 27 * 512
+    attn_frame = 8.154e9 / 24
+    spatial_frame = HW * (lin_tok + peg_tok) + attn_frame
+    dense, execd, n = 0.0, 0.0, 0
+    for t0 in range(T - nt + 1):
+        frames = sum(min(nt + 2 * (l + 1), T - t0) for l in range(n_layers))
+        n_hw = 23 * 23
+        dense += n_hw * FLOP_FWD
+        execd += n_hw * (FLOP_FWD - 56.62e9 - (n_layers * T - frames) * spatial_frame)
+        n += n_hw
+    return dense + FLOP_FWD, execd + FLOP_FWD, n
+
+
+def run_attribution(eng, host_vol, tl, dev, world, dist):
+    """BASELINE.json's first metric: attributed CT volumes/s = one 480x480x240 volume through the full occlusion
+    sweep ((20,40,40)/(10,20,20): 12 167 windows, visualizations.py:335-424) plus 50-step integrated gradients
+    (:851-901), windows and alpha steps sharded over the N ranks, scores / partial gradient sums combined with
+    NCCL.  End to end: the timed region starts from the pinned host volume and ends with both maps on the host."""
+    import torch
+    from ctclip_b200 import attribution as A
+
+    def once():
+        t0 = time.perf_counter()
+        vol = host_vol.to(dev, non_blocking=True)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        heat, aux = A.occlusion_sensitivity(eng, vol, tl)
+        e[1].record()
+        ig, _ = A.integrated_gradients(eng, vol, tl, steps=50, batch=5)
+        e[2].record()
+        out = (heat.cpu(), ig.cpu())
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        return wall, e[0].elapsed_time(e[1]) / 1e3, e[1].elapsed_time(e[2]) / 1e3, int(aux["included"].sum()), out
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall, occ_s, ig_s, n_win, _ = once()
+    t = torch.tensor([wall, occ_s, ig_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, occ_s, ig_s = (float(v) for v in t)
+    dense, execd, _ = occlusion_flops()
+    ig_flop = 50 * (FLOP_FWD + FLOP_BWD)
+    peak = load_peaks()["tf"] * 1e12 * world
+    return {"metric": "attributed_volumes_per_sec", "value": 1.0 / wall, "unit": "volumes/s", "scaling": "strong",
+            "seconds_per_volume": wall, "occlusion_s": occ_s, "ig_s": ig_s, "windows": n_win, "ig_steps": 50,
+            "h2d_bytes": int(host_vol.numel() * 4), "d2h_bytes": int(2 * host_vol.numel() * 4),
+            "occlusion_mode": "frame reuse: patch embedding + unreachable spatial frames from the baseline cache",
+            "dense_equiv_pflop": (dense + ig_flop) / 1e15, "executed_pflop": (execd + ig_flop) / 1e15,
+            "frac_of_tensor_peak_executed": (execd + ig_flop) / (occ_s + ig_s) / peak,
+            "timing": "wall clock incl. H2D of the volume and D2H of both maps, max over ranks; one un-warmed pass "
+                      "after the fwd+bwd benchmark warmed the kernels"}
+
+
 # ------------------------------------------------------------------------------------------ product arm
 def run_product(args):
     import torch
@@ -278,6 +340,13 @@ def run_product(args):
                 "launches_per_step": len(events), "gemm_ms_per_step": gemm_ms,
                 "share_of_step": gemm_ms / ms_step}
 
+    # ---- the attribution sub-metric (occlusion sweep + IG-50 of one volume, sharded over the ranks)
+    attribution = None
+    if not args.no_attribution:
+        del bufs, vol, grad, ctx, graph
+        torch.cuda.empty_cache()
+        attribution = run_attribution(eng, host[:1], tl, dev, world, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -308,6 +377,8 @@ def run_product(args):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
+    if attribution is not None:
+        out["attribution"] = attribution
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -320,6 +391,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-attribution", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

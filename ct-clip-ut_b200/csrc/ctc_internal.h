@@ -13,6 +13,6 @@ int num_sms();
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldc, int M, int N,
               int K, int epi, const float* bias, const float* resid, long long ldr, void* aux, long long ldaux,
               float* top2_val, int* top2_idx, int impl, cudaStream_t st);
-int gemm_argmax_tiles(int N);
+int gemm_argmax_candidates(int N);
 
 }  // namespace ctc

@@ -2,6 +2,8 @@
 // stencil (+adjoint), GEGLU fwd/bwd, continuous-position-bias table.
 // All are bandwidth kernels: 128-bit vector accesses, one warp per 512-wide row, warp-shuffle
 // reductions, grids sized well above 148 SMs x resident CTAs.
+#include <limits.h>
+
 #include "common.cuh"
 #include "ctc_internal.h"
 
@@ -110,47 +112,84 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 //   TEMPORAL: (t',h',w') = (h, w, t)  =>  (dt, dh, dw) = (c-1, a-2, b-1)
 // The adjoint (sign = -1) gathers with the negated offsets.
 //
-// HBM-bound design (28 MB in / 28 MB out per volume): a naive 27-tap gather re-reads every input
-// 27x through L2 and is L2-bandwidth bound.  Here a thread owns ONE channel and walks along w with a
-// 9-row x 3-column register window (9 new 4-byte loads per output instead of 27; a warp's 32 lanes
-// are 32 consecutive channels = one 128-byte line per load), the 27 weights live in registers, and
-// the 16 warps of a CTA cover a 2 (t) x 8 (h) tile of the same channel chunk so that the remaining
-// 9x row reuse is served by L1.
+// HBM-bound target (28 MB in / 28 MB out per volume).  What actually limits a stencil like this on
+// sm_100 is instruction issue: 27 FMAs per output on the fma pipe (one 3-register FFMA per 2 cycles per
+// SM sub-partition) and one LSU slot per global load.  So a thread owns a channel PAIR and
+//   * every load is a 64-bit LDG (a warp covers 64 consecutive channels = two 128-byte lines),
+//   * every multiply-add is a packed FFMA2 (fma.rn.f32x2: two fp32 FMAs per issue slot),
+//   * it walks along w with a 9-row x 3-column register window (9 new loads per output pair instead
+//     of 27) rotating through 5 column slots, so two columns of loads are always in flight,
+//   * the 27 weight pairs live in registers, and the 12 warps of a CTA cover a 2 (t) x 6 (h) tile of
+//     the same channel chunk so that the remaining 9x row reuse is served by L1.
 // ---------------------------------------------------------------------------------------------
-static constexpr int PEG_TT = 2, PEG_TH = 8;
+static constexpr int PEG_TT = 2, PEG_TH = 6;
+typedef unsigned long long f32x2;   // two packed fp32 (lo = even channel)
+
+CTC_DEVINL f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+CTC_DEVINL f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+CTC_DEVINL f32x2 pack2(float lo, float hi) {
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+CTC_DEVINL float2 unpack2(f32x2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
 
 // One output column.  A,B,D are the register columns holding x[w-1], x[w], x[w+1] for the 9 (dt,dh) rows;
-// N is the column slot being (re)filled with x[w+4] (three columns stay in flight: w+2, w+3, w+4).
-// With the 6-slot rotation fully unrolled no register moves remain, and with a compile-time channel count
+// N is the column slot being (re)filled with x[w+3] (two columns stay in flight: w+2, w+3).
+// With the 5-slot rotation fully unrolled no register moves remain, and with a compile-time channel count
 // every load/store of an unrolled block is "base register + immediate".
-#define PEG_STEP(A, B, D, N, WOFF, LOADCOL)                                                        \
+#define PEG_STEP(A, B, D, N, WOFF, LOADCOL)                                                          \
     {                                                                                                \
         const int wc = w0 + (WOFF);                                                                  \
         if (LOADCOL) {                                                                               \
-            _Pragma("unroll") for (int k9 = 0; k9 < 9; ++k9) N[k9] = rp[k9][(long long)(wc + 4) * CS]; \
+            _Pragma("unroll") for (int k9 = 0; k9 < 9; ++k9)                                         \
+                N[k9] = *reinterpret_cast<const f32x2*>(rp[k9] + (long long)(wc + 3) * CS);          \
         } else {                                                                                     \
-            _Pragma("unroll") for (int k9 = 0; k9 < 9; ++k9) N[k9] = 0.f;                            \
+            _Pragma("unroll") for (int k9 = 0; k9 < 9; ++k9) N[k9] = 0ull;                           \
         }                                                                                            \
-        float acc = B[7] + bv, acc1 = 0.f, acc2 = 0.f;                                               \
+        f32x2 acc = fadd2(B[7], bv), acc1 = 0ull, acc2 = 0ull;                                       \
         _Pragma("unroll") for (int k9 = 0; k9 < 9; ++k9) {                                           \
-            acc = fmaf(wk[k9][0], A[k9], acc);                                                       \
-            acc1 = fmaf(wk[k9][1], B[k9], acc1);                                                     \
-            acc2 = fmaf(wk[k9][2], D[k9], acc2);                                                     \
+            acc = ffma2(wk[k9][0], A[k9], acc);                                                      \
+            acc1 = ffma2(wk[k9][1], B[k9], acc1);                                                    \
+            acc2 = ffma2(wk[k9][2], D[k9], acc2);                                                    \
         }                                                                                            \
-        acc += acc1 + acc2;                                                                          \
-        yo[(long long)wc * CS] = acc;                                                                \
-        if (BF16OUT) yb[(long long)wc * CS] = __float2bfloat16(acc);                                 \
+        acc = fadd2(acc, fadd2(acc1, acc2));                                                         \
+        *reinterpret_cast<f32x2*>(yo + (long long)wc * CS) = acc;                                    \
+        if (BF16OUT) {                                                                               \
+            const float2 af = unpack2(acc);                                                          \
+            *reinterpret_cast<uint32_t*>(yb + (long long)wc * CS) = pack_bf16(af.x, af.y);           \
+        }                                                                                            \
     }
 
-// CC = compile-time channel count (0: runtime); SIGN = +1 forward, -1 adjoint; BF16OUT = also emit a bf16 copy
-template <int CC, int SIGN, bool BF16OUT>
+// CC, CW = compile-time channel count / row length (0: runtime); SIGN = +1 forward, -1 adjoint;
+// BF16OUT = also emit a bf16 copy.
+// FRAMES (forward, spatial mode only): the stencil runs over a COMPACT list of T output frames whose three
+// causal source frames (dt = -2,-1,0) come from a table: frame_src[f*3 + k] >= 0 selects frame v of `x`,
+// v < 0 selects frame (-1 - v) of `xb`, INT_MIN is the causal zero pad.  This is what lets an occlusion window
+// recompute only the frames its cube can reach (the causal stencil widens the changed set by two frames per
+// layer) and read every other frame from the cached baseline activations.
+template <int CC, int CW, int SIGN, bool BF16OUT, bool FRAMES>
 __global__ void __launch_bounds__(PEG_TT * PEG_TH * 32)
 peg_kernel(const float* __restrict__ x, int B, int T, int H, int W, int C, const float* __restrict__ w27,
-           const float* __restrict__ bias, int mode, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16) {
+           const float* __restrict__ bias, int mode, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
+           const float* __restrict__ xb, const int* __restrict__ frame_src) {
     constexpr int sign = SIGN;
     const int CS = CC ? CC : C;
+    if (CW) W = CW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
+    const int c = blockIdx.x * 64 + lane * 2;
     const int h = blockIdx.y * PEG_TH + (warp % PEG_TH);
     const int tiles_t = (T + PEG_TT - 1) / PEG_TT;
     const int t = (blockIdx.z % tiles_t) * PEG_TT + warp / PEG_TH;
@@ -158,64 +197,100 @@ peg_kernel(const float* __restrict__ x, int B, int T, int H, int W, int C, const
     if (h >= H || t >= T || c >= CS) return;
     // weights wk[k9][cw] for the 9 non-w taps x 3 w taps; rows outside the grid alias the centre row with
     // zero weights, so that every load of the main loop is unconditional
-    float wk[9][3];
+    f32x2 wk[9][3];
     const float* rp[9];
-    const float* self = x + ((((long long)b * T + t) * H + h) * W) * CS + c;
+    const long long frame = (long long)H * W * CS;
+    const float* fbase[3] = {nullptr, nullptr, nullptr};
+    if (FRAMES) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int v = frame_src[t * 3 + k];
+            fbase[k] = (v == INT_MIN) ? nullptr : (v >= 0 ? x + v * frame : xb + (long long)(-1 - v) * frame);
+        }
+    }
+    const float* self = FRAMES ? fbase[2] + (long long)h * W * CS + c
+                               : x + ((((long long)b * T + t) * H + h) * W) * CS + c;
 #pragma unroll
     for (int k9 = 0; k9 < 9; ++k9) {
         const int p = k9 / 3, q = k9 % 3;
         int dt, dh;
-        if (mode == CTC_MODE_SPATIAL) { dt = p - 2; dh = q - 1; } else { dh = p - 2; dt = q - 1; }
+        if (FRAMES || mode == CTC_MODE_SPATIAL) { dt = p - 2; dh = q - 1; } else { dh = p - 2; dt = q - 1; }
         const int tt = t + sign * dt, hh = h + sign * dh;
-        const bool valid = tt >= 0 && tt < T && hh >= 0 && hh < H;
+        const bool valid = FRAMES ? (fbase[p] != nullptr && hh >= 0 && hh < H)
+                                  : (tt >= 0 && tt < T && hh >= 0 && hh < H);
 #pragma unroll
         for (int cw = 0; cw < 3; ++cw) {
             // the adjoint reads x[w - (cw - 1)]: store its w-taps mirrored so that the step body is identical
             const int cwm = (SIGN > 0) ? cw : 2 - cw;
-            const int tap = (mode == CTC_MODE_SPATIAL) ? (p * 3 + q) * 3 + cwm : (p * 3 + cwm) * 3 + q;
-            wk[k9][cw] = valid ? w27[tap * CS + c] : 0.f;
+            const int tap = (FRAMES || mode == CTC_MODE_SPATIAL) ? (p * 3 + q) * 3 + cwm : (p * 3 + cwm) * 3 + q;
+            wk[k9][cw] = valid ? *reinterpret_cast<const f32x2*>(w27 + tap * CS + c) : 0ull;
         }
-        rp[k9] = valid ? x + ((((long long)b * T + tt) * H + hh) * W) * CS + c : self;
+        if (FRAMES) rp[k9] = valid ? fbase[p] + (long long)hh * W * CS + c : self;
+        else rp[k9] = valid ? x + ((((long long)b * T + tt) * H + hh) * W) * CS + c : self;
     }
-    const float bv = (bias && sign > 0) ? bias[c] : 0.f;
-    float* yo = y + (self - x);
-    __nv_bfloat16* yb = BF16OUT ? y_bf16 + (self - x) : nullptr;
+    const f32x2 bv = (bias && sign > 0) ? *reinterpret_cast<const f32x2*>(bias + c) : 0ull;
+    const long long out_off = FRAMES ? ((long long)t * H + h) * W * CS + c : (self - x);
+    float* yo = y + out_off;
+    __nv_bfloat16* yb = BF16OUT ? y_bf16 + out_off : nullptr;
     // k9 = 7 is the (dt, dh) = (0, 0) row: B[7] is the residual term x[w] (its weights are always valid)
-    float c0[9], c1[9], c2[9], c3[9], c4[9], c5[9];
+    f32x2 c0[9], c1[9], c2[9], c3[9], c4[9];
 #pragma unroll
     for (int k9 = 0; k9 < 9; ++k9) {
-        c0[k9] = 0.f;                                          // x[-1]
-        c1[k9] = rp[k9][0];
-        c2[k9] = (W > 1) ? rp[k9][(long long)1 * CS] : 0.f;
-        c3[k9] = (W > 2) ? rp[k9][(long long)2 * CS] : 0.f;
-        c4[k9] = (W > 3) ? rp[k9][(long long)3 * CS] : 0.f;
-        c5[k9] = 0.f;
+        c0[k9] = 0ull;                                          // x[-1]
+        c1[k9] = *reinterpret_cast<const f32x2*>(rp[k9]);
+        c2[k9] = (W > 1) ? *reinterpret_cast<const f32x2*>(rp[k9] + (long long)1 * CS) : 0ull;
+        c3[k9] = (W > 2) ? *reinterpret_cast<const f32x2*>(rp[k9] + (long long)2 * CS) : 0ull;
+        c4[k9] = 0ull;
     }
     int w0 = 0;
-    for (; w0 + 6 + 4 <= W; w0 += 6) {          // every column w0+4 .. w0+9 is inside the row: unconditional loads
-        PEG_STEP(c0, c1, c2, c5, 0, true)
+#pragma unroll
+    for (; w0 + 5 + 3 <= W; w0 += 5) {          // every column w0+3 .. w0+7 is inside the row: unconditional loads
+        PEG_STEP(c0, c1, c2, c4, 0, true)
         PEG_STEP(c1, c2, c3, c0, 1, true)
         PEG_STEP(c2, c3, c4, c1, 2, true)
-        PEG_STEP(c3, c4, c5, c2, 3, true)
-        PEG_STEP(c4, c5, c0, c3, 4, true)
-        PEG_STEP(c5, c0, c1, c4, 5, true)
+        PEG_STEP(c3, c4, c0, c2, 3, true)
+        PEG_STEP(c4, c0, c1, c3, 4, true)
     }
-    for (; w0 < W; w0 += 6) {                   // tail block(s): guard loads and stores
+#pragma unroll
+    for (; w0 < W; w0 += 5) {                   // tail block(s): guard loads and stores
 #define PEG_TAIL(A, B, D, N, WOFF)                                     \
         if (w0 + (WOFF) < W) {                                         \
-            if (w0 + (WOFF) + 4 < W) PEG_STEP(A, B, D, N, WOFF, true)  \
+            if (w0 + (WOFF) + 3 < W) PEG_STEP(A, B, D, N, WOFF, true)  \
             else PEG_STEP(A, B, D, N, WOFF, false)                     \
         }
-        PEG_TAIL(c0, c1, c2, c5, 0)
+        PEG_TAIL(c0, c1, c2, c4, 0)
         PEG_TAIL(c1, c2, c3, c0, 1)
         PEG_TAIL(c2, c3, c4, c1, 2)
-        PEG_TAIL(c3, c4, c5, c2, 3)
-        PEG_TAIL(c4, c5, c0, c3, 4)
-        PEG_TAIL(c5, c0, c1, c4, 5)
+        PEG_TAIL(c3, c4, c0, c2, 3)
+        PEG_TAIL(c4, c0, c1, c3, 4)
 #undef PEG_TAIL
     }
 }
 #undef PEG_STEP
+
+// ---------------------------------------------------------------------------------------------
+// Frame plumbing of the occlusion fast path: gather whole frames from two sources, overwrite token rows.
+// ---------------------------------------------------------------------------------------------
+// out frame f = (src[f] >= 0) ? a[src[f]] : b[-1 - src[f]]      (frame = frame_elems fp32, multiple of 4)
+__global__ void __launch_bounds__(256)
+frames_gather_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const int* __restrict__ src,
+                     long long frame_vec4, float4* __restrict__ out) {
+    const int f = blockIdx.y;
+    const int v = src[f];
+    const float4* s = (v >= 0) ? a + (long long)v * frame_vec4 : b + (long long)(-1 - v) * frame_vec4;
+    float4* o = out + (long long)f * frame_vec4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < frame_vec4;
+         i += (long long)gridDim.x * blockDim.x)
+        o[i] = s[i];
+}
+// x[rows[r], :] = value[:]
+__global__ void rows_fill_kernel(float* __restrict__ x, const int* __restrict__ rows, int n_rows, int C,
+                                 const float* __restrict__ value) {
+    const int r = blockIdx.x;
+    if (r >= n_rows) return;
+    float* xr = x + (long long)rows[r] * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) xr[c] = value[c];
+}
 
 // ---------------------------------------------------------------------------------------------
 // GEGLU
@@ -325,23 +400,64 @@ extern "C" int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, 
 extern "C" int ctc_peg(const float* x, int B, int T, int H, int W, int C, const float* w27, const float* bias,
                        int mode, int transpose, float* y, void* y_bf16, void* stream) {
     CTC_REQUIRE(x != y, "peg: in-place stencil is not supported");
+    CTC_REQUIRE(C % 2 == 0, "peg: C=%d must be even (threads own channel pairs)", C);
     CTC_REQUIRE(mode == CTC_MODE_SPATIAL || (T == H && H == W),
                 "peg: temporal mode reinterprets (h,w,t) as (t,h,w) and needs T==H==W (got %d,%d,%d)", T, H, W);
     const int tiles_t = (T + PEG_TT - 1) / PEG_TT;
     CTC_REQUIRE((long long)B * tiles_t <= 65535, "peg: batch %d too large for one launch", B);
-    dim3 grid((C + 31) / 32, (H + PEG_TH - 1) / PEG_TH, B * tiles_t);
+    dim3 grid((C + 63) / 64, (H + PEG_TH - 1) / PEG_TH, B * tiles_t);
     const int threads = PEG_TT * PEG_TH * 32;
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* yb = (__nv_bfloat16*)y_bf16;
-#define PEG_LAUNCH(CC, SG, BF) peg_kernel<CC, SG, BF><<<grid, threads, 0, st>>>(x, B, T, H, W, C, w27, bias, mode, y, yb)
-    if (C == 512) {
-        if (!transpose) { if (yb) PEG_LAUNCH(512, 1, true); else PEG_LAUNCH(512, 1, false); }
-        else            { if (yb) PEG_LAUNCH(512, -1, true); else PEG_LAUNCH(512, -1, false); }
+#define PEG_LAUNCH(CC, CW, SG, BF) \
+    peg_kernel<CC, CW, SG, BF, false><<<grid, threads, 0, st>>>(x, B, T, H, W, C, w27, bias, mode, y, yb, nullptr, nullptr)
+    if (C == 512 && W == 24) {     // the CTViT geometry: every offset of the unrolled walk is an immediate
+        if (!transpose) { if (yb) PEG_LAUNCH(512, 24, 1, true); else PEG_LAUNCH(512, 24, 1, false); }
+        else            { if (yb) PEG_LAUNCH(512, 24, -1, true); else PEG_LAUNCH(512, 24, -1, false); }
     } else {
-        if (!transpose) { if (yb) PEG_LAUNCH(0, 1, true); else PEG_LAUNCH(0, 1, false); }
-        else            { if (yb) PEG_LAUNCH(0, -1, true); else PEG_LAUNCH(0, -1, false); }
+        if (!transpose) { if (yb) PEG_LAUNCH(0, 0, 1, true); else PEG_LAUNCH(0, 0, 1, false); }
+        else            { if (yb) PEG_LAUNCH(0, 0, -1, true); else PEG_LAUNCH(0, 0, -1, false); }
     }
 #undef PEG_LAUNCH
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_peg_frames(const float* x_changed, const float* x_base, const int* frame_src, int F, int H, int W,
+                              int C, const float* w27, const float* bias, float* y, void* stream) {
+    CTC_REQUIRE(F > 0 && C % 2 == 0, "peg_frames: F=%d must be positive and C=%d even", F, C);
+    CTC_REQUIRE(y != x_changed && y != x_base, "peg_frames: in-place stencil is not supported");
+    const int tiles_t = (F + PEG_TT - 1) / PEG_TT;
+    CTC_REQUIRE(tiles_t <= 65535, "peg_frames: %d frames are too many for one launch", F);
+    dim3 grid((C + 63) / 64, (H + PEG_TH - 1) / PEG_TH, tiles_t);
+    const int threads = PEG_TT * PEG_TH * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 512 && W == 24)
+        peg_kernel<512, 24, 1, false, true><<<grid, threads, 0, st>>>(x_changed, 1, F, H, W, C, w27, bias,
+                                                                       CTC_MODE_SPATIAL, y, nullptr, x_base, frame_src);
+    else
+        peg_kernel<0, 0, 1, false, true><<<grid, threads, 0, st>>>(x_changed, 1, F, H, W, C, w27, bias,
+                                                                   CTC_MODE_SPATIAL, y, nullptr, x_base, frame_src);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_frames_gather(const float* a, const float* b, const int* src, int F, int64_t frame_elems,
+                                 float* out, void* stream) {
+    CTC_REQUIRE(F > 0 && frame_elems > 0 && frame_elems % 4 == 0, "frames_gather: F=%d, frame_elems=%lld (multiple of 4)",
+                F, (long long)frame_elems);
+    CTC_REQUIRE(F <= 65535, "frames_gather: %d frames are too many for one launch", F);
+    const long long v4 = frame_elems / 4;
+    const int bx = (int)((v4 + 255) / 256 < 64 ? (v4 + 255) / 256 : 64);
+    frames_gather_kernel<<<dim3(bx, F), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), src, v4, reinterpret_cast<float4*>(out));
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_rows_fill(float* x, const int* rows, int n_rows, int C, const float* value, void* stream) {
+    CTC_REQUIRE(n_rows > 0 && C > 0, "rows_fill: n_rows=%d, C=%d", n_rows, C);
+    rows_fill_kernel<<<n_rows, 128, 0, (cudaStream_t)stream>>>(x, rows, n_rows, C, value);
     CTC_LAUNCH_CHECK();
     return 0;
 }

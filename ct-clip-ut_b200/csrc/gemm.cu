@@ -4,7 +4,10 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma kind::f16, M=128, N=BN, K=16)
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4-7   epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global); a warp may
+//               only touch TMEM lanes 32*(warp%4)..+31, so warps w and w+4 share a lane quarter and
+//               split the tile's columns in halves: the epilogues that do real arithmetic per element
+//               (GEGLU, VQ top-2) and the residual loads get 8 warps of issue slots / loads in flight
 // The accumulator lives in TMEM and is double buffered, so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Both operands are K-major ("row-major [rows, K]"), which is exactly the
 // nn.Linear weight layout [out_features, in_features] (reference: src/utils/attention.py:47,49,
@@ -20,7 +23,8 @@ namespace ctc {
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 static constexpr int kStages = 4;
-static constexpr int kGemmThreads = 256;
+static constexpr int kEpiWarps = 8;
+static constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 
 struct GemmArgs {
     int M, N, K;
@@ -41,7 +45,7 @@ struct GemmSmem {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStageOut = 4 * 4096;               // epilogue staging: 4 warps x (32 rows x 128 B)
+    static constexpr int kStageOut = kEpiWarps * 4096;       // epilogue staging: per warp 32 rows x 128 B
     static constexpr int kOutOffset = kStages * kStageBytes;
     static constexpr int kBarOffset = kOutOffset + kStageOut;
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
@@ -241,7 +245,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
@@ -299,7 +303,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
-        const int ew = warp - 4;  // TMEM lane quarter: warp (id % 4) may only touch lanes 32*(id%4)..+31
+        const int ew = (warp - 4) & 3;   // TMEM lane quarter: warp (id % 4) may only touch lanes 32*(id%4)..+31
+        const int eh = (warp - 4) >> 2;  // which half of the tile's columns this warp owns
+        constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+        const int cbeg = eh * kColsPerWarp, cend = cbeg + kColsPerWarp;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tm = tile / tiles_n, tn = tile % tiles_n;
@@ -307,7 +314,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tcgen05_fence_after();
             const int row = tm * BM + ew * 32 + lane;
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
-            uint8_t* stage = smem + S::kOutOffset + ew * 4096;
+            uint8_t* stage = smem + S::kOutOffset + (warp - 4) * 4096;
             const int row0 = tm * BM + ew * 32;
             if constexpr (EPI == CTC_EPI_ARGMAX) {
                 // four independent trackers break the 256-long dependent compare chain
@@ -316,7 +323,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int i = 0; i < 4; ++i) t2[i].init();
                 const bool full = (tn + 1) * BN <= g.N;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = cbeg; c < cend; c += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c, v);
                     tmem_ld_wait();
@@ -328,7 +335,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int i = 1; i < 4; ++i) { t2[0].push(t2[i].v0, t2[i].i0); t2[0].push(t2[i].v1, t2[i].i1); }
                 if (row < g.M) {
-                    const long long o = ((long long)row * g.n_tiles_n + tn) * 2;
+                    const long long o = (((long long)row * g.n_tiles_n + tn) * (kEpiWarps / 4) + eh) * 2;
                     g.top2_val[o] = t2[0].v0; g.top2_val[o + 1] = t2[0].v1;
                     g.top2_idx[o] = t2[0].i0; g.top2_idx[o + 1] = t2[0].i1;
                 }
@@ -338,7 +345,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 __nv_bfloat16* hout = reinterpret_cast<__nv_bfloat16*>(g.out);
                 __nv_bfloat16* uout = reinterpret_cast<__nv_bfloat16*>(g.aux);
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 64) {
+                for (int c = cbeg; c < cend; c += 64) {
                     const int col0 = tn * BN + c;
                     if (col0 >= g.N) break;
                     uint32_t xv[32], gv[32];
@@ -367,7 +374,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const __nv_bfloat16* uin = reinterpret_cast<const __nv_bfloat16*>(g.aux);
                 __nv_bfloat16* duout = reinterpret_cast<__nv_bfloat16*>(g.out);
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = cbeg; c < cend; c += 32) {
                     const int col0 = tn * BN + c;
                     if (col0 >= g.N) break;
                     stage_load_bf16_64(g, stage, row0, 2 * col0, lane, uin, g.ldaux);
@@ -396,7 +403,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                      (!g.resid || ((g.ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(g.resid) & 15) == 0)) &&
                                      (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = cbeg; c < cend; c += 32) {
                     const int col0 = tn * BN + c;
                     if (col0 >= g.N) break;
                     const bool fast = aligned && (col0 + 32 <= g.N);
@@ -411,7 +418,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             } else {
                 const bool aligned = (g.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0);
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 64) {
+                for (int c = cbeg; c < cend; c += 64) {
                     const int col0 = tn * BN + c;
                     if (col0 >= g.N) break;
                     uint32_t v[32], pk[32];
@@ -596,6 +603,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
     return 0;
 }
 
-int gemm_argmax_tiles(int N) { return (N + 255) / 256; }
+// candidates per row left by the ARGMAX epilogue: top-2 of every (256 / halves)-code slice
+int gemm_argmax_candidates(int N) { return ((N + 255) / 256) * (kEpiWarps / 4) * 2; }
 
 }  // namespace ctc

@@ -323,16 +323,18 @@ extern "C" int ctc_latent_sim_bwd(const float* latent, const float* text_latents
     return 0;
 }
 
+extern "C" int ctc_vq_num_candidates(int K) { return gemm_argmax_candidates(K); }
+
 extern "C" int ctc_vq_argmax(const float* x, const void* x_bf16, int R, int C, const float* codebook,
                              const void* codebook_bf16, int K, float* cand_val, int* cand_idx, int* ind,
                              void* stream) {
     CTC_REQUIRE(C % 4 == 0, "vq: C=%d must be a multiple of 4", C);
-    const int n_tiles = gemm_argmax_tiles(K);
+    const int n_cand = gemm_argmax_candidates(K);
     if (int e = gemm_bf16(x_bf16, C, codebook_bf16, C, nullptr, 0, R, K, C, CTC_EPI_ARGMAX, nullptr, nullptr, 0, nullptr, 0,
                           cand_val, cand_idx, CTC_GEMM_TCGEN05, (cudaStream_t)stream))
         return e;
     vq_refine_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, R, C, codebook, cand_val, cand_idx,
-                                                                    n_tiles * 2, ind);
+                                                                    n_cand, ind);
     CTC_LAUNCH_CHECK();
     return 0;
 }

@@ -27,6 +27,9 @@ SIGNATURES = {
     "ctc_layernorm_fwd": [P, I, I, P, P, F, P, P, P, P],
     "ctc_layernorm_bwd": [P, P, I, I, P, F, P, I, P, P],
     "ctc_peg": [P, I, I, I, I, I, P, P, I, I, P, P, P],
+    "ctc_peg_frames": [P, P, P, I, I, I, I, P, P, P, P],
+    "ctc_frames_gather": [P, P, P, I, L, P, P],
+    "ctc_rows_fill": [P, P, I, I, P, P],
     "ctc_attention_fwd": [P, L, P, P, L, I, I, I, I, I, P, P, F, P, I, P, P, P],
     "ctc_attention_bwd": [P, L, P, P, L, P, P, P, I, I, I, I, I, P, P, F, P, I, P, L, P, P, L, P, P],
     "ctc_attention_probs": [P, L, P, L, P, I, I, I, I, I, P, P, F, P, I, P, P],
@@ -55,7 +58,7 @@ SIGNATURES = {
     "ctc_occlusion_heatmap": [P, P, I, I, I, I, I, I, I, I, I, I, I, I, P, P],
 }
 OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, []),
-                 "ctc_launch_count": (ctypes.c_longlong, [])}
+                 "ctc_launch_count": (ctypes.c_longlong, []), "ctc_vq_num_candidates": (c_int, [c_int])}
 
 EPI_BF16, EPI_F32, EPI_ARGMAX, EPI_GEGLU, EPI_GEGLU_BWD = 0, 1, 2, 3, 4
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
@@ -111,6 +114,11 @@ def call(name: str, *args) -> None:
     rc = getattr(lib, name)(*[ptr(a) for a in args])
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.ctc_last_error().decode(errors='replace')}")
+
+
+def vq_num_candidates(codebook_size: int) -> int:
+    """Width of the candidate scratch ctc_vq_argmax expects (include/ctclip_b200.h)."""
+    return int(load().ctc_vq_num_candidates(int(codebook_size)))
 
 
 def launch_count() -> int:

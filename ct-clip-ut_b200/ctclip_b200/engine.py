@@ -14,6 +14,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -44,6 +45,7 @@ class Ctx:
     alpha: Optional[torch.Tensor] = None
     x_lin: torch.Tensor = None                 # patch-embedding Linear output (input of LayerNorm(dim))
     x_in: torch.Tensor = None                  # tokens entering the spatial transformer
+    spatial_in: List[torch.Tensor] = field(default_factory=list)   # keep_stream: input of each spatial layer
     spatial: List[LayerCtx] = field(default_factory=list)
     temporal: List[LayerCtx] = field(default_factory=list)
     x_s_last: torch.Tensor = None              # stream leaving the last spatial layer (input of norm_out)
@@ -60,6 +62,66 @@ class Ctx:
     tokens: Optional[torch.Tensor] = None      # fp32 [R, C] quantised tokens (optional)
     # gradient captures for Grad-CAM (visualizations.py:140-218): grads of the residual stream
     grads: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+
+@dataclass
+class OcclusionCache:
+    """Baseline activations an occlusion sweep re-uses for every window (Engine.occlusion_baseline)."""
+    T: int = 0
+    spatial_in: List[torch.Tensor] = field(default_factory=list)   # fp32 [T*HW, C]: input of each spatial layer
+    x_s_out: torch.Tensor = None                                   # fp32 [T*HW, C]: spatial norm_out output
+    e_mask: torch.Tensor = None                                    # fp32 [C]: token embedding of a fully occluded patch
+    sim: torch.Tensor = None                                       # fp32 [1, Bt]: un-occluded logits
+
+
+INT_MIN = -2 ** 31
+
+
+def occlusion_frame_tables(cubes, cube_shape, T: int, H: int, n_layers: int):
+    """Host-side index tables of Engine.forward_occluded for a batch of occlusion cubes.
+
+    cubes int [Wn,3] = (t0,h0,w0) token coordinates, cube_shape = (nt,nh,nw).  The changed frames of window w
+    entering spatial layer l are t0 .. t0+n_l-1 with n_0 = nt and n_{l+1} = min(n_l + 2, T - t0): the causal
+    stencil reads frames t-2..t, so a changed frame t' reaches t', t'+1, t'+2 (attention.py:55-83,
+    ctvit.py:60-61).  Compact buffers hold the windows' changed frames back to back.  Returns
+    ([src0, rows, peg_src_0 .. peg_src_{L-1}, full], [F_0 .. F_{L-1}]) as int64 arrays:
+      src0      [Wn*nt]     baseline frames to copy as layer-0 input, encoded -1 - t
+      rows      [Wn*nt*nh*nw] token rows of the compact layer-0 input covered by the cube
+      peg_src_l [F_l*3]     per output frame the source of dt = -2,-1,0: >= 0 compact frame of the previous
+                            buffer, < 0 baseline frame -1 - t, INT_MIN causal zero padding
+      full      [Wn*T]      per (window, t): compact frame of the last buffer or baseline -1 - t"""
+    nt, nh, nw = cube_shape
+    HW = H * H
+    cubes = np.asarray(cubes, dtype=np.int64).reshape(-1, 3)
+    Wn = len(cubes)
+    t0 = cubes[:, 0]
+    n_prev = np.full(Wn, nt, dtype=np.int64)
+    off_prev = np.arange(Wn, dtype=np.int64) * nt
+    tables = [(-1 - (t0[:, None] + np.arange(nt)[None, :])).reshape(-1)]
+    jt, jh, jw = np.meshgrid(np.arange(nt), np.arange(nh), np.arange(nw), indexing="ij")
+    rows = ((off_prev[:, None] + jt.reshape(1, -1)) * HW + (cubes[:, 1:2] + jh.reshape(1, -1)) * H
+            + cubes[:, 2:3] + jw.reshape(1, -1)).reshape(-1)
+    tables.append(rows)
+    layer_F = []
+    for _ in range(n_layers):
+        n_out = np.minimum(n_prev + 2, T - t0)
+        off_out = np.concatenate([[0], np.cumsum(n_out)[:-1]])
+        F = int(n_out.sum())
+        widx = np.repeat(np.arange(Wn), n_out)
+        i = np.arange(F) - off_out[widx]                       # frame offset inside the window's changed set
+        src = np.empty((F, 3), dtype=np.int64)
+        for k, dt in enumerate((-2, -1, 0)):
+            ip = i + dt                                        # offset of the source frame relative to t0
+            tt = t0[widx] + ip
+            in_prev = (ip >= 0) & (ip < n_prev[widx])
+            src[:, k] = np.where(tt < 0, INT_MIN, np.where(in_prev, off_prev[widx] + ip, -1 - tt))
+        tables.append(src.reshape(-1))
+        layer_F.append(F)
+        n_prev, off_prev = n_out, off_out
+    tt = np.arange(T)[None, :] - t0[:, None]                                           # [Wn, T]
+    full = np.where((tt >= 0) & (tt < n_prev[:, None]), off_prev[:, None] + tt, -1 - np.arange(T)[None, :])
+    tables.append(full.reshape(-1))
+    return tables, layer_F
 
 
 class Engine:
@@ -101,16 +163,25 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ one transformer layer
-    def _layer_fwd(self, x0, lw: LayerWeights, B, T, mode, save: bool) -> Tuple[torch.Tensor, LayerCtx]:
+    def _layer_fwd(self, x0, lw: LayerWeights, B, T, mode, save: bool, frames=None) -> Tuple[torch.Tensor, LayerCtx]:
+        """One transformer layer.  `frames` = (x_base, frame_src int32 [F,3]) runs the PEG stencil over a compact
+        frame list (occlusion fast path): x0 holds the changed frames of the previous layer, the output has
+        B*T = F frames."""
         cfg = self.cfg
-        R, C = x0.shape
+        C = x0.shape[1]
         H = W = cfg.hw
+        R = B * T * H * W
         inner, FP = cfg.inner, cfg.ff_pad
         bf = torch.bfloat16
         lc = LayerCtx()
         # x = peg(x) + x                                                   attention.py:325
         x1 = self._empty(R, C)
-        call("ctc_peg", x0, B, T, H, W, C, lw.w27, lw.peg_bias, mode, 0, x1, None, stream_ptr())
+        if frames is None:
+            assert x0.shape[0] == R
+            call("ctc_peg", x0, B, T, H, W, C, lw.w27, lw.peg_bias, mode, 0, x1, None, stream_ptr())
+        else:
+            assert mode == MODE_SPATIAL and B == 1
+            call("ctc_peg_frames", x0, frames[0], frames[1], T, H, W, C, lw.w27, lw.peg_bias, x1, stream_ptr())
         # attention: q from LayerNorm(x), k/v from the RAW x                attention.py:138-142
         xn, xraw = self._empty(R, C, dtype=bf), self._empty(R, C, dtype=bf)
         self.layernorm(x1, lw.ln_g, lw.ln_b, y_bf16=xn, xraw=xraw)
@@ -143,10 +214,11 @@ class Engine:
     def forward(self, volume: torch.Tensor, text_latents: Optional[torch.Tensor], batch: Optional[int] = None,
                 alpha: Optional[torch.Tensor] = None, occl: Optional[torch.Tensor] = None,
                 occl_value: float = -1.0, save: bool = False, want_tokens: bool = False,
-                keep_attn: bool = False) -> Ctx:
+                keep_attn: bool = False, keep_stream: bool = False, stop_after_patch_emb: bool = False) -> Ctx:
         """volume fp32 [Bv, 1, D, H, W] (Bv == batch, or Bv == 1 shared by all `batch` rows: windows /
         alpha steps of one volume).  alpha fp32 [batch] (IG interpolation), occl int32 [batch, 6]
-        (occlusion cubes).  `save` keeps what backward needs; `keep_attn` keeps q/kv/lse only (rollout)."""
+        (occlusion cubes).  `save` keeps what backward needs; `keep_attn` keeps q/kv/lse only (rollout);
+        `keep_stream` keeps the input of every spatial layer and the spatial output (occlusion baseline cache)."""
         cfg, pl = self.cfg, self.plan
         assert volume.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous()
         Bv, _, D, Hv, Wv = volume.shape
@@ -169,15 +241,31 @@ class Engine:
         self.layernorm(x_lin, pl.pe_ln2_w, pl.pe_ln2_b, y_f32=x)
         if save:
             ctx.x_lin, ctx.x_in = x_lin, x
+        if stop_after_patch_emb:
+            ctx.x_in = x
+            return ctx
 
         # spatial transformer over '(b t) (h w) d'                               ctvit.py:94-96
         for lw in pl.spatial:
+            if keep_stream:
+                ctx.spatial_in.append(x)
             x, lc = self._layer_fwd(x, lw, B, T, MODE_SPATIAL, keep)
             ctx.spatial.append(lc)
         xs = self._empty(R, C)
         self.layernorm(x, pl.spatial_norm_g, pl.spatial_norm_b, y_f32=xs)
         if save:
-            ctx.x_s_last, ctx.x_s_out = x, xs
+            ctx.x_s_last = x
+        if save or keep_stream:
+            ctx.x_s_out = xs
+        return self._forward_tail(ctx, xs, text_latents, save, keep, want_tokens)
+
+    def _forward_tail(self, ctx: Ctx, xs: torch.Tensor, text_latents: Optional[torch.Tensor], save: bool, keep: bool,
+                      want_tokens: bool) -> Ctx:
+        """Temporal transformer, VQ and CLIP head on the spatial transformer's output xs fp32 [R, C]."""
+        cfg, pl = self.cfg, self.plan
+        B, T, H = ctx.B, ctx.T, cfg.hw
+        R, C = xs.shape
+        bf = torch.bfloat16
         x = xs
         # temporal transformer over '(b h w) t d'                                ctvit.py:99-101
         for lw in pl.temporal:
@@ -191,7 +279,7 @@ class Engine:
 
         # VQ (cosine codebook, arg-max)                                           ctvit.py:115-118
         K = cfg.codebook_size
-        n_cand = ((K + 255) // 256) * 2
+        n_cand = _lib.vq_num_candidates(K)
         cand_val = self._empty(R, n_cand)
         cand_idx = self._empty(R, n_cand, dtype=torch.int32)
         ind = self._empty(R, dtype=torch.int32)
@@ -217,6 +305,62 @@ class Engine:
         ctx.latent, ctx.image_latents, ctx.sim, ctx.dlatent = latent, il, sim, dlat
         ctx.text_latents = text_latents
         return ctx
+
+    # ------------------------------------------------------------------ occlusion fast path
+    def occlusion_baseline(self, volume: torch.Tensor, text_latents: torch.Tensor, fill: float = -1.0
+                           ) -> OcclusionCache:
+        """Un-occluded forward of ONE volume that keeps what every occlusion window can re-use: the input of
+        each spatial layer, the spatial output, and the embedding of a patch filled with `fill`
+        (LayerNorm of a constant patch is exactly its bias, so that embedding is position independent)."""
+        cfg = self.cfg
+        assert volume.shape[0] == 1
+        ctx = self.forward(volume, text_latents, keep_stream=True)
+        D = volume.shape[2]
+        tp, ps = cfg.temporal_patch_size, cfg.patch_size
+        win = torch.tensor([[0, 0, 0, tp, ps, ps]], dtype=torch.int32, device=self.dev)
+        pe = self.forward(volume, None, batch=1, occl=win, occl_value=fill, stop_after_patch_emb=True)
+        return OcclusionCache(T=D // tp, spatial_in=ctx.spatial_in, x_s_out=ctx.x_s_out, e_mask=pe.x_in[0].clone(),
+                              sim=ctx.sim)
+
+    def forward_occluded(self, cache: OcclusionCache, cubes, cube_shape, text_latents: torch.Tensor) -> Ctx:
+        """Forward of len(cubes) occluded copies of the cached volume.  cubes: int [Wn, 3] token coordinates
+        (t0, h0, w0) of each occlusion cube, cube_shape = (nt, nh, nw) tokens (visualizations.py:380-381 with
+        token-aligned windows).  Identical arithmetic to forward(occl=...), but only the frames a cube can reach
+        are recomputed in the spatial transformer: its one cross-frame operator is the causal PEG stencil
+        (attention.py:55-83, ctvit.py:60-61), so after layer l the changed frames are t0 .. t0+nt-1+2(l+1);
+        every other frame is read from the baseline cache.  The temporal transformer, VQ and head run in full."""
+        cfg, pl = self.cfg, self.plan
+        T, H = cache.T, cfg.hw
+        HW, C = H * H, cfg.dim
+        nt, nh, nw = cube_shape
+        cubes = np.asarray(cubes, dtype=np.int64).reshape(-1, 3)
+        Wn = len(cubes)
+        t0 = cubes[:, 0]
+        assert (t0 >= 0).all() and (t0 + nt <= T).all() and (cubes[:, 1:] >= 0).all()
+        assert (cubes[:, 1] + nh <= H).all() and (cubes[:, 2] + nw <= H).all()
+        # ---- host-side frame tables for the whole batch, one upload
+        tables, layer_F = occlusion_frame_tables(cubes, cube_shape, T, H, len(pl.spatial))
+        rows = tables[1]
+        sizes = [len(a) for a in tables]
+        packed = torch.from_numpy(np.concatenate(tables).astype(np.int32)).to(self.dev, non_blocking=True)
+        views, o = [], 0
+        for n in sizes:
+            views.append(packed[o:o + n])
+            o += n
+        # ---- changed input frames: baseline tokens with the cube's rows replaced by the occluded-patch embedding
+        x = self._empty(Wn * nt * HW, C)
+        call("ctc_frames_gather", None, cache.spatial_in[0], views[0], Wn * nt, HW * C, x, stream_ptr())
+        call("ctc_rows_fill", x, views[1], len(rows), C, cache.e_mask, stream_ptr())
+        ctx = Ctx(B=Wn, T=T)
+        for l, lw in enumerate(pl.spatial):
+            x, _ = self._layer_fwd(x, lw, 1, layer_F[l], MODE_SPATIAL, False,
+                                   frames=(cache.spatial_in[l], views[2 + l]))
+        xs_c = self._empty(x.shape[0], C)
+        self.layernorm(x, pl.spatial_norm_g, pl.spatial_norm_b, y_f32=xs_c)
+        xs = self._empty(Wn * T * HW, C)
+        call("ctc_frames_gather", xs_c, cache.x_s_out, views[-1], Wn * T, HW * C, xs, stream_ptr())
+        del x, xs_c
+        return self._forward_tail(ctx, xs, text_latents, False, False, False)
 
     # ------------------------------------------------------------------ backward
     def _layer_bwd(self, dx3, dx3_bf, lc: LayerCtx, lw: LayerWeights, B, T, mode, capture: Optional[dict], tag: str):

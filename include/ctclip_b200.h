@@ -84,6 +84,20 @@ int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, const float
 int ctc_peg(const float* x, int B, int T, int H, int W, int C, const float* w27, const float* bias, int mode,
             int transpose, float* y, void* y_bf16, void* stream);
 
+/* Occlusion fast path (visualizations.py:335-392 evaluates one full forward per window; a window only
+ * changes the tokens of its cube, and the spatial transformer's only cross-frame operator is the CAUSAL
+ * depthwise stencil, so the changed frame set grows by two frames per layer and every other frame equals
+ * the cached baseline).  ctc_peg_frames is ctc_peg (forward, SPATIAL) over a compact list of F output
+ * frames: frame_src int32 [F,3] names the source frame for dt = -2,-1,0: v >= 0 -> frame v of x_changed,
+ * v < 0 -> frame (-1 - v) of x_base, INT_MIN -> causal zero padding.  y fp32 [F, H, W, C].
+ * ctc_frames_gather: out[f] = src[f] >= 0 ? a[src[f]] : b[-1 - src[f]] (frames of frame_elems fp32).
+ * ctc_rows_fill: x[rows[r], :] = value[:] (the embedding of a fully occluded patch). */
+int ctc_peg_frames(const float* x_changed, const float* x_base, const int* frame_src, int F, int H, int W, int C,
+                   const float* w27, const float* bias, float* y, void* stream);
+int ctc_frames_gather(const float* a, const float* b, const int* src, int F, int64_t frame_elems, float* out,
+                      void* stream);
+int ctc_rows_fill(float* x, const int* rows, int n_rows, int C, const float* value, void* stream);
+
 /* Cosine-similarity attention core (attention.py:144-180): per (sequence, head)
  * softmax(scale * l2norm(q)*q_scale . l2norm(k)*k_scale + bias) v.  q bf16 [R, heads*32] (stride ldq),
  * k/v bf16 (stride ldkv; v = k + heads*32 columns).  SPATIAL: sequences are the (b,t) slices of
@@ -117,9 +131,10 @@ int ctc_cpb_table(const float* w0, const float* b0, const float* w1, const float
                   const float* b2, int dim, int heads, int H, int W, float* table, void* stream);
 
 /* VQ nearest-code search (ctvit.py:117-118; vector_quantize_pytorch cosine codebook):
- * cand_val/cand_idx = per-256-code-tile top-2 of the bf16 score GEMM (ctc_gemm_bf16 epi ARGMAX
- * is run internally); candidates within a rounding margin of the best are re-scored in fp32
- * against the fp32 codebook, so the arg-max is exact w.r.t. x.  ind int32 [R]. */
+ * cand_val/cand_idx [R, ctc_vq_num_candidates(K)] scratch = top-2 of every 128-code slice of the bf16
+ * score GEMM (ctc_gemm_bf16 epi ARGMAX is run internally); candidates within a rounding margin of the
+ * best are re-scored in fp32 against the fp32 codebook, so the arg-max is exact w.r.t. x.  ind int32 [R]. */
+int ctc_vq_num_candidates(int K);
 int ctc_vq_argmax(const float* x, const void* x_bf16, int R, int C, const float* codebook,
                   const void* codebook_bf16, int K, float* cand_val, int* cand_idx, int* ind, void* stream);
 /* pooled[b,hw,c] = mean_t E[ind[b,t,hw]][c] (ctclip.py:111) fp32 (+bf16 copy); tokens fp32 [R,C] optional. */

@@ -122,6 +122,28 @@ def test_occlusion_coarse_vs_reference_golden(setup):
     assert float(np.abs(heat.cpu().numpy() - ref).max()) < 1e-5
 
 
+def test_occlusion_reuse_equals_dense_forward(setup):
+    """The frame-reuse fast path (Engine.forward_occluded) must give the same logits and the same VQ codes as
+    a full forward with the cube fused into the patch-embedding load, for reference-sized windows
+    (20,40,40) at the volume corners, the centre and the last frames (clipped changed-frame sets)."""
+    from ctclip_b200 import attribution as A
+    eng, vol, tl, _, _ = setup
+    ps = (20, 40, 40)
+    windows = [(0, 0, 0), (220, 440, 440), (100, 200, 220), (210, 0, 440), (10, 20, 20), (150, 440, 0), (220, 0, 0)]
+    o_fast, s_fast = A.occlusion_scores(eng, vol, tl, windows, ps, reuse=True, reuse_batch=4)
+    o_dense, s_dense = A.occlusion_scores(eng, vol, tl, windows, ps, reuse=False, batch=4)
+    print(f"[occlusion reuse] orig {o_fast:.7f} / {o_dense:.7f}\n  fast  {s_fast.cpu().numpy()}\n  dense {s_dense.cpu().numpy()}")
+    assert o_fast == o_dense
+    assert float((s_fast - s_dense).abs().max()) < 1e-6
+    cache = eng.occlusion_baseline(vol, tl)
+    cubes = [[d // 10, h // 20, w // 20] for (d, h, w) in windows[:3]]
+    ctx_f = eng.forward_occluded(cache, cubes, (2, 2, 2), tl)
+    wins = torch.tensor([[d, h, w, *ps] for (d, h, w) in windows[:3]], dtype=torch.int32, device=DEV)
+    ctx_d = eng.forward(vol, tl, batch=3, occl=wins)
+    assert torch.equal(ctx_f.indices, ctx_d.indices)
+    assert torch.equal(ctx_f.x_pre_vq, ctx_d.x_pre_vq)
+
+
 def test_occlusion_heatmap_default_grid_vs_oracle():
     """12 167-window grid, random scores, shard with dropped remainder: bit-exact masks / counts."""
     from ctclip_b200 import attribution as A

@@ -108,8 +108,8 @@ def test_layernorm_fwd_bwd(lib, R, C):
 
 # --------------------------------------------------------------------------------------- PEG
 @pytest.mark.parametrize("mode", [0, 1])
-def test_peg_fwd_and_adjoint(lib, mode):
-    B, T, H, W, C = 2, 6, 6, 6, 64
+@pytest.mark.parametrize("B,T,H,W,C", [(2, 6, 6, 6, 64), (1, 24, 24, 24, 512), (2, 5, 5, 5, 66), (1, 7, 7, 7, 2)])
+def test_peg_fwd_and_adjoint(lib, mode, B, T, H, W, C):
     x = rnd(B * T * H * W, C, seed=1)
     w = rnd(C, 1, 3, 3, 3, seed=2, scale=0.2)
     bias = rnd(C, seed=3, scale=0.1)
@@ -132,6 +132,56 @@ def test_peg_fwd_and_adjoint(lib, mode):
     lib.call("ctc_peg", dy, B, T, H, W, C, w27, None, mode, 1, dx, d16, lib.stream_ptr())
     assert relerr(dx, dx_ref) < 1e-5
     assert relerr(d16, dx_ref) < 1e-2
+
+
+@pytest.mark.parametrize("T,H,W,C", [(9, 6, 6, 64), (24, 24, 24, 512)])
+def test_peg_frames_matches_dense_peg(lib, T, H, W, C):
+    """ctc_peg_frames over a compact frame list (changed frames of two 'windows' + baseline frames for the rest)
+    must reproduce exactly the dense spatial PEG of the volumes one would assemble by hand."""
+    import numpy as np
+    HW = H * W
+    base = rnd(T * HW, C, seed=1)                      # baseline stream of one volume
+    w27 = rnd(C, 27, seed=2, scale=0.2).t().contiguous()
+    bias = rnd(C, seed=3, scale=0.1)
+    wins = [(0, 2), (T - 3, 3), (3, 2)]                # (t0, n_prev changed input frames)
+    n_prev = [n for _, n in wins]
+    off_prev = np.concatenate([[0], np.cumsum(n_prev)[:-1]])
+    changed = rnd(sum(n_prev) * HW, C, seed=4)
+    src, expect = [], []
+    for wi, (t0, n) in enumerate(wins):
+        full = base.clone().view(T, HW, C)
+        full[t0:t0 + n] = changed.view(-1, HW, C)[off_prev[wi]:off_prev[wi] + n]
+        yfull = torch.empty(T * HW, C, device=dev())
+        lib.call("ctc_peg", full.reshape(-1, C).contiguous(), 1, T, H, W, C, w27, bias, 0, 0, yfull, None, lib.stream_ptr())
+        n_out = min(n + 2, T - t0)
+        for i in range(n_out):
+            row = []
+            for dt in (-2, -1, 0):
+                ip, tt = i + dt, t0 + i + dt
+                row.append(-2 ** 31 if tt < 0 else (int(off_prev[wi] + ip) if 0 <= ip < n else -1 - tt))
+            src.append(row)
+            expect.append(yfull.view(T, HW, C)[t0 + i])
+    src_t = torch.tensor(src, dtype=torch.int32, device=dev())
+    F_ = len(src)
+    y = torch.full((F_ * HW, C), float("nan"), device=dev())
+    lib.call("ctc_peg_frames", changed, base, src_t, F_, H, W, C, w27, bias, y, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(F_, HW, C), torch.stack(expect))
+
+
+def test_frames_gather_and_rows_fill(lib):
+    a, b = rnd(5 * 96, 8, seed=1), rnd(7 * 96, 8, seed=2)
+    src = torch.tensor([0, -1, 4, -7, 2], dtype=torch.int32, device=dev())
+    out = torch.empty(5 * 96, 8, device=dev())
+    lib.call("ctc_frames_gather", a, b, src, 5, 96 * 8, out, lib.stream_ptr())
+    ref = torch.stack([a.view(5, -1)[0], b.view(7, -1)[0], a.view(5, -1)[4], b.view(7, -1)[6], a.view(5, -1)[2]])
+    assert torch.equal(out.view(5, -1), ref)
+    rows = torch.tensor([3, 100, 479], dtype=torch.int32, device=dev())
+    val = rnd(8, seed=3)
+    lib.call("ctc_rows_fill", out, rows, 3, 8, val, lib.stream_ptr())
+    ref2 = ref.reshape(-1, 8).clone()
+    ref2[rows.long()] = val
+    assert torch.equal(out, ref2)
 
 
 # --------------------------------------------------------------------------------------- attention
@@ -329,7 +379,7 @@ def test_vq_argmax_gather_bwd(lib):
     B, T, HW = 2, 10, 100
     x = rnd(R, C, seed=1)
     cb = F.normalize(rnd(K, C, seed=2), dim=-1)
-    n_cand = (K + 255) // 256 * 2
+    n_cand = lib.vq_num_candidates(K)
     cv = torch.empty(R, n_cand, device=dev())
     ci = torch.empty(R, n_cand, device=dev(), dtype=torch.int32)
     ind = torch.empty(R, device=dev(), dtype=torch.int32)
