@@ -403,6 +403,10 @@ extern "C" int ctc_peg(const float* x, int B, int T, int H, int W, int C, const 
     CTC_REQUIRE(C % 2 == 0, "peg: C=%d must be even (threads own channel pairs)", C);
     CTC_REQUIRE(mode == CTC_MODE_SPATIAL || (T == H && H == W),
                 "peg: temporal mode reinterprets (h,w,t) as (t,h,w) and needs T==H==W (got %d,%d,%d)", T, H, W);
+    {   // bulk-asynchronous halo-tile kernel (peg_tma.cu) whenever the geometry allows it
+        const int e = peg_tma_launch(x, B, T, H, W, C, w27, bias, mode, transpose, y, y_bf16, (cudaStream_t)stream);
+        if (e >= 0) return e;
+    }
     const int tiles_t = (T + PEG_TT - 1) / PEG_TT;
     CTC_REQUIRE((long long)B * tiles_t <= 65535, "peg: batch %d too large for one launch", B);
     dim3 grid((C + 63) / 64, (H + PEG_TH - 1) / PEG_TH, B * tiles_t);
