@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(HPC * (QB / 16) * 32, (HPC * (QB / 16) * 32 <=
 attn_fwd_kernel(const AttnParams p) {
     extern __shared__ __align__(128) uint8_t sm[];
     constexpr int WPH = QB / 16;
-    const int qb = blockIdx.z, head0 = blockIdx.y * HPC, s = blockIdx.x;
+    const int head0 = blockIdx.y * HPC, s = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hl = warp / WPH, wq = warp % WPH, head = head0 + hl;
     const int kv_bytes = p.n_pad * 64;
@@ -190,16 +190,20 @@ attn_fwd_kernel(const AttnParams p) {
     __syncthreads();
     load_tile<true>(ks, kv_bytes, p.k, p.ldkv, p, s, head0, HPC, 0, p.n_pad, sv + 32, 1.0f);
     if (!PROBS) load_tile<false>(vs, kv_bytes, p.v, p.ldkv, p, s, head0, HPC, 0, p.n_pad, nullptr, 1.0f);
+    const uint32_t ks_a = smem_u32(ks + hl * kv_bytes), vs_a = smem_u32(vs + hl * kv_bytes);
+    const uint32_t qs_a = smem_u32(qs + hl * QB * 64);
+    const int g = lane >> 2, t = lane & 3;
+    // K/V of the (sequence, head) stay resident; the CTA walks the query blocks gridDim.z apart (gridDim.z = 1:
+    // one K/V load + normalisation per (sequence, head) instead of one per query block)
+  for (int qb = blockIdx.z; qb * QB < p.n; qb += gridDim.z) {
+    __syncthreads();                                    // previous block's Q fragments are in registers
     load_tile<true>(qs, QB * 64, p.q, p.ldq, p, s, head0, HPC, qb * QB, QB, sv, p.scale * LOG2E);
     __syncthreads();
 
     const int row_base = qb * QB + wq * 16;
-    if (row_base >= p.n) return;
-    const uint32_t ks_a = smem_u32(ks + hl * kv_bytes), vs_a = smem_u32(vs + hl * kv_bytes);
-    const uint32_t qs_a = smem_u32(qs + hl * QB * 64);
+    if (row_base >= p.n) continue;
     uint32_t aq[2][4];
     load_a_frags(aq, qs_a, wq * 16, lane);
-    const int g = lane >> 2, t = lane & 3;
     const int i0 = row_base + g, i1 = i0 + 8;
     const bool has_bias = p.bias_table != nullptr;
     const int base0 = has_bias ? bias_base(p, i0) : 0, base1 = has_bias ? bias_base(p, i1) : 0;
@@ -276,7 +280,7 @@ attn_fwd_kernel(const AttnParams p) {
             mma_colsB(oacc, a, vs_a, kb * KBLK + kk * 16, lane);
         }
     }
-    if (PROBS) return;
+    if (PROBS) continue;
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.f / l0, inv1 = 1.f / l1;
@@ -296,6 +300,7 @@ attn_fwd_kernel(const AttnParams p) {
             *reinterpret_cast<uint32_t*>(orow + a * 8 + 2 * t) = pack_bf16(oacc[a][2] * inv1, oacc[a][3] * inv1);
         if (t == 0) p.lse[r * p.heads + head] = (m1 + log2f(l1)) * LN2;
     }
+  }
 }
 
 // adjoint of x^ = l2norm(x) * vec for one row held in mma C layout (quad of lanes owns the row):
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(HPC * (QB / 16) * 32, (HPC * (QB / 16) * 32 <=
 attn_bwd_dq_kernel(const AttnParams p) {
     extern __shared__ __align__(128) uint8_t sm[];
     constexpr int WPH = QB / 16;
-    const int qb = blockIdx.z, head0 = blockIdx.y * HPC, s = blockIdx.x;
+    const int head0 = blockIdx.y * HPC, s = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hl = warp / WPH, wq = warp % WPH, head = head0 + hl;
     const int kv_bytes = p.n_pad * 64;
@@ -350,6 +355,14 @@ attn_bwd_dq_kernel(const AttnParams p) {
     __syncthreads();
     load_tile<true>(ks, kv_bytes, p.k, p.ldkv, p, s, head0, HPC, 0, p.n_pad, sv + 32, 1.0f);
     load_tile<false>(vs, kv_bytes, p.v, p.ldkv, p, s, head0, HPC, 0, p.n_pad, nullptr, 1.0f);
+    const uint32_t ks_a = smem_u32(ks + hl * kv_bytes), vs_a = smem_u32(vs + hl * kv_bytes);
+    const uint32_t qs_a = smem_u32(qs + hl * QB * 64), dos_a = smem_u32(dos + hl * QB * 64);
+    const int g = lane >> 2, t = lane & 3;
+    const bool has_bias = p.bias_table != nullptr;
+    const bool need_mask = (p.n % KBLK) != 0;
+  // K/V stay resident; the CTA walks the query blocks gridDim.z apart
+  for (int qb = blockIdx.z; qb * QB < p.n; qb += gridDim.z) {
+    __syncthreads();
     load_tile<true>(qs, QB * 64, p.q, p.ldq, p, s, head0, HPC, qb * QB, QB, sv, p.scale * LOG2E);
     load_tile<false>(dos, QB * 64, p.d_o, (long long)p.heads * DH, p, s, head0, HPC, qb * QB, QB, nullptr, 1.0f);
     // D_i = sum_d dO_i,d * O_i,d   (thread per (row, head))
@@ -378,17 +391,12 @@ attn_bwd_dq_kernel(const AttnParams p) {
     __syncthreads();
 
     const int row_base = qb * QB + wq * 16;
-    if (row_base >= p.n) return;
-    const uint32_t ks_a = smem_u32(ks + hl * kv_bytes), vs_a = smem_u32(vs + hl * kv_bytes);
-    const uint32_t qs_a = smem_u32(qs + hl * QB * 64), dos_a = smem_u32(dos + hl * QB * 64);
+    if (row_base >= p.n) continue;
     uint32_t aq[2][4], ado[2][4];
     load_a_frags(aq, qs_a, wq * 16, lane);
     load_a_frags(ado, dos_a, wq * 16, lane);
-    const int g = lane >> 2, t = lane & 3;
     const int i0 = row_base + g, i1 = i0 + 8;
-    const bool has_bias = p.bias_table != nullptr;
     const int base0 = has_bias ? bias_base(p, i0) : 0, base1 = has_bias ? bias_base(p, i1) : 0;
-    const bool need_mask = (p.n % KBLK) != 0;
     const float lse2_0 = (i0 < p.n) ? p.lse[seq_row(p, s, i0) * p.heads + head] * LOG2E : INFINITY;
     const float lse2_1 = (i1 < p.n) ? p.lse[seq_row(p, s, i1) * p.heads + head] * LOG2E : INFINITY;
     const float d0 = dl[hl * QB + wq * 16 + g], d1 = dl[hl * QB + wq * 16 + g + 8];
@@ -440,6 +448,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
         for (int a = 0; a < 4; ++a)
             *reinterpret_cast<uint32_t*>(drow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(HPC * (QB / 16) * 32, (HPC * (QB / 16) * 32 <=
 attn_bwd_dkv_kernel(const AttnParams p) {
     extern __shared__ __align__(128) uint8_t sm[];
     constexpr int WPH = QB / 16;
-    const int kblk = blockIdx.z, head0 = blockIdx.y * HPC, s = blockIdx.x;
+    const int head0 = blockIdx.y * HPC, s = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hl = warp / WPH, wq = warp % WPH, head = head0 + hl;
     const int kv_bytes = p.n_pad * 64;
@@ -484,20 +493,23 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     __syncthreads();
     load_tile<true>(qs, kv_bytes, p.q, p.ldq, p, s, head0, HPC, 0, p.n_pad, sv, p.scale * LOG2E);
     load_tile<false>(dos, kv_bytes, p.d_o, (long long)p.heads * DH, p, s, head0, HPC, 0, p.n_pad, nullptr, 1.0f);
+    const uint32_t ks_a = smem_u32(ks + hl * QB * 64), vs_a = smem_u32(vs + hl * QB * 64);
+    const uint32_t qs_a = smem_u32(qs + hl * kv_bytes), dos_a = smem_u32(dos + hl * kv_bytes);
+    const float* lse2h = lse2 + hl * p.n_pad;
+    const float* dlh = dl + hl * p.n_pad;
+    const int g = lane >> 2, t = lane & 3;
+  // Q / dO / lse / delta of the (sequence, head) stay resident; the CTA walks the key blocks gridDim.z apart
+  for (int kblk = blockIdx.z; kblk * QB < p.n; kblk += gridDim.z) {
+    __syncthreads();
     load_tile<true>(ks, QB * 64, p.k, p.ldkv, p, s, head0, HPC, kblk * QB, QB, sv + 32, 1.0f);
     load_tile<false>(vs, QB * 64, p.v, p.ldkv, p, s, head0, HPC, kblk * QB, QB, nullptr, 1.0f);
     __syncthreads();
 
     const int row_base = kblk * QB + wq * 16;
-    if (row_base >= p.n) return;
-    const uint32_t ks_a = smem_u32(ks + hl * QB * 64), vs_a = smem_u32(vs + hl * QB * 64);
-    const uint32_t qs_a = smem_u32(qs + hl * kv_bytes), dos_a = smem_u32(dos + hl * kv_bytes);
-    const float* lse2h = lse2 + hl * p.n_pad;
-    const float* dlh = dl + hl * p.n_pad;
+    if (row_base >= p.n) continue;
     uint32_t ak[2][4], av[2][4];
     load_a_frags(ak, ks_a, wq * 16, lane);
     load_a_frags(av, vs_a, wq * 16, lane);
-    const int g = lane >> 2, t = lane & 3;
     const int j0 = row_base + g, j1 = j0 + 8;
     int tab0 = 0, tab1 = 0;
     if (has_bias) {
@@ -566,6 +578,7 @@ attn_bwd_dkv_kernel(const AttnParams p) {
         for (int a = 0; a < 4; ++a)
             *reinterpret_cast<uint32_t*>(dkrow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -596,17 +609,25 @@ static int launch_attn(const AttnParams& p, dim3 grid, int threads, size_t smem,
 // small-sequence configuration (temporal, n <= 32): all heads of a sequence in one CTA when heads % 8 == 0
 static bool use_small(const AttnParams& p) { return p.n <= 32 && p.bias_table == nullptr; }
 
+// Row blocks of one (sequence, head) are walked by ONE CTA (gridDim.z = 1, resident K/V or Q/dO loaded and
+// normalised once) whenever the other grid dimensions already fill the machine; small launches keep one CTA
+// per block for parallelism.
+static int attn_grid_z(const AttnParams& p, int qb) {
+    const int blocks = (p.n + qb - 1) / qb;
+    return ((long long)p.n_seq * p.heads >= 2ll * num_sms()) ? 1 : blocks;
+}
+
 template <int QB, int KBLK, int HPC, bool PROBS>
 static int run_fwd(AttnParams& p, cudaStream_t st) {
     const size_t nb = p.bias_table ? (size_t)(2 * p.H - 1) * (2 * p.W - 1) : 0;
     const size_t smem = (size_t)HPC * (p.n_pad * 128 + QB * 64) + 256 + p.n_pad * 4 + nb * 4;
-    dim3 grid(p.n_seq, p.heads / HPC, (p.n + QB - 1) / QB);
+    dim3 grid(p.n_seq, p.heads / HPC, attn_grid_z(p, QB));
     return launch_attn<attn_fwd_kernel<QB, KBLK, HPC, PROBS>>(p, grid, HPC * (QB / 16) * 32, smem, st);
 }
 template <int QB, int KBLK, int HPC>
 static int run_bwd(AttnParams& p, cudaStream_t st) {
     const size_t nb = p.bias_table ? (size_t)(2 * p.H - 1) * (2 * p.W - 1) : 0;
-    dim3 grid(p.n_seq, p.heads / HPC, (p.n + QB - 1) / QB);
+    dim3 grid(p.n_seq, p.heads / HPC, attn_grid_z(p, QB));
     const size_t smem_dq = (size_t)HPC * (p.n_pad * 128 + 2 * QB * 64 + QB * 4) + 256 + p.n_pad * 4 + nb * 4;
     if (int e = launch_attn<attn_bwd_dq_kernel<QB, KBLK, HPC>>(p, grid, HPC * (QB / 16) * 32, smem_dq, st)) return e;
     const size_t smem_dkv = (size_t)HPC * (p.n_pad * 128 + 2 * QB * 64 + 2 * p.n_pad * 4) + 256 + p.n_pad * 4 + nb * 4;

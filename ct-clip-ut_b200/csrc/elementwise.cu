@@ -104,6 +104,62 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     }
 }
 
+// C = 512 specialisation: the row (16 floats per lane) and its gradient live in registers, so every global
+// load of a row (x, dy, the accumulate target) is issued up front and nothing is re-read.  Same summation
+// order as the generic kernel (bit-identical results).
+template <bool ACC, bool BF16OUT>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_c512_kernel(const float* __restrict__ dy, const float* __restrict__ x, int R,
+                          const float* __restrict__ gamma, float eps, float* __restrict__ out,
+                          __nv_bfloat16* __restrict__ out_bf16) {
+    constexpr int C = 512;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const long long base = (long long)row * C + lane * 4;
+    float4 v[4], d[4], gm[4], pr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = *reinterpret_cast<const float4*>(x + base + 128 * k);
+        d[k] = *reinterpret_cast<const float4*>(dy + base + 128 * k);
+        if (ACC) pr[k] = *reinterpret_cast<const float4*>(out + base + 128 * k);
+        gm[k] = *reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * k);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = v[k].x - mean, b = v[k].y - mean, cc = v[k].z - mean, e = v[k].w - mean;
+        q += (a * a + b * b) + (cc * cc + e * e);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float g0 = d[k].x * gm[k].x, g1 = d[k].y * gm[k].y, g2 = d[k].z * gm[k].z, g3 = d[k].w * gm[k].w;
+        sg += (g0 + g1) + (g2 + g3);
+        sgx += g0 * (v[k].x - mean) * rstd + g1 * (v[k].y - mean) * rstd + g2 * (v[k].z - mean) * rstd +
+               g3 * (v[k].w - mean) * rstd;
+    }
+    sg = warp_sum(sg) / C;
+    sgx = warp_sum(sgx) / C;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float4 o;
+        o.x = rstd * (d[k].x * gm[k].x - sg - (v[k].x - mean) * rstd * sgx);
+        o.y = rstd * (d[k].y * gm[k].y - sg - (v[k].y - mean) * rstd * sgx);
+        o.z = rstd * (d[k].z * gm[k].z - sg - (v[k].z - mean) * rstd * sgx);
+        o.w = rstd * (d[k].w * gm[k].w - sg - (v[k].w - mean) * rstd * sgx);
+        if (ACC) { o.x += pr[k].x; o.y += pr[k].y; o.z += pr[k].z; o.w += pr[k].w; }
+        *reinterpret_cast<float4*>(out + base + 128 * k) = o;
+        if (BF16OUT)
+            *reinterpret_cast<uint2*>(out_bf16 + base + 128 * k) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // PEG: depthwise 3x3x3 stencil over the token grid, channels-last.
 // Kernel tap (a, b, c) (the Conv3d kernel indices over the reinterpreted (t',h',w') axes, with
@@ -391,8 +447,22 @@ extern "C" int ctc_layernorm_fwd(const float* x, int R, int C, const float* gamm
 extern "C" int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, const float* gamma, float eps,
                                  float* out, int accumulate, void* out_bf16, void* stream) {
     CTC_REQUIRE(C % 4 == 0 && R > 0, "layernorm_bwd: C=%d must be a multiple of 4, R=%d > 0", C, R);
-    layernorm_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dy, x, R, C, gamma, eps, out, accumulate,
-                                                                        (__nv_bfloat16*)out_bf16);
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16* ob = (__nv_bfloat16*)out_bf16;
+    const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                      reinterpret_cast<uintptr_t>(gamma)) & 15) == 0 && (reinterpret_cast<uintptr_t>(ob) & 7) == 0;
+    if (C == 512 && al) {
+        const int grid = (R + 7) / 8;
+        if (accumulate) {
+            if (ob) layernorm_bwd_c512_kernel<true, true><<<grid, 256, 0, st>>>(dy, x, R, gamma, eps, out, ob);
+            else layernorm_bwd_c512_kernel<true, false><<<grid, 256, 0, st>>>(dy, x, R, gamma, eps, out, ob);
+        } else {
+            if (ob) layernorm_bwd_c512_kernel<false, true><<<grid, 256, 0, st>>>(dy, x, R, gamma, eps, out, ob);
+            else layernorm_bwd_c512_kernel<false, false><<<grid, 256, 0, st>>>(dy, x, R, gamma, eps, out, ob);
+        }
+    } else {
+        layernorm_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(dy, x, R, C, gamma, eps, out, accumulate, ob);
+    }
     CTC_LAUNCH_CHECK();
     return 0;
 }
