@@ -269,10 +269,11 @@ static int make_geom(PatchGeom& g, long long vol_stride, int B, int D, int H, in
     CTC_REQUIRE(p % 4 == 0, "patchify: patch size %d must be a multiple of 4 (128-bit loads)", p);
     g.B = B; g.D = D; g.H = H; g.W = W; g.pt = pt; g.p = p;
     g.T = D / pt; g.Hp = H / p; g.Wp = W / p; g.P = pt * p * p; g.vol_stride = vol_stride;
-    // patches per CTA: largest divisor of Wp with tile <= 96 KB and <= 32 patches
+    // patches per CTA: largest divisor of Wp with tile <= 50 KB (four resident CTAs per SM overlap their
+    // load / statistics / store phases; two 96 KB CTAs left DRAM at 35 % in ncu) and <= 32 patches
     int G = 1;
     for (int c = 1; c <= g.Wp && c <= 32; ++c)
-        if (g.Wp % c == 0 && (long long)c * g.P * bytes_per_elem <= 100 * 1024 && c * p <= 1024) G = c;
+        if (g.Wp % c == 0 && (long long)c * g.P * bytes_per_elem <= 50 * 1024 && c * p <= 1024) G = c;
     g.G = G;
     CTC_REQUIRE((long long)G * g.P * bytes_per_elem <= 200 * 1024, "patchify: patch of %d voxels does not fit shared memory", g.P);
     CTC_REQUIRE(g.P % 8 == 0, "patchify: patch volume %d must be a multiple of 8", g.P);
@@ -292,6 +293,8 @@ extern "C" int ctc_patchify_ln_fwd(const float* volume, int64_t vol_batch_stride
     static size_t configured = 0;
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            (int)cudaSharedmemCarveoutMaxShared));
         configured = smem;
     }
     const long long grid = (long long)B * g.T * g.Hp * (g.Wp / g.G);
@@ -310,6 +313,8 @@ extern "C" int ctc_patchify_ln_bwd(const float* volume, int64_t vol_batch_stride
     static size_t configured = 0;
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            (int)cudaSharedmemCarveoutMaxShared));
         configured = smem;
     }
     const long long grid = (long long)B * g.T * g.Hp * (g.Wp / g.G);

@@ -125,9 +125,13 @@ def quantile_linear(x: torch.Tensor, q: float) -> float:
 # ------------------------------------------------------------------------------------------- occlusion
 def occlusion_scores(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor, windows: Sequence,
                      patch_size, batch: int = 8, fill: float = -1.0, reuse: Optional[bool] = None,
-                     reuse_batch: int = 32) -> Tuple[float, torch.Tensor]:
+                     reuse_batch: int = 32, all_prompts: bool = False):
     """Baseline score and one score per window (visualizations.py:370-388).  Returns (orig, scores fp32
     [len(windows)] on device).  Perturbed volumes are never materialised.
+
+    all_prompts=True scores every row of text_latents [P, NL] from the SAME image forward (the image tower does
+    not depend on the prompt): returns (orig fp32 [P], scores fp32 [len(windows), P]) — the reference runs one
+    complete sweep per pathology prompt (visualizations.py:1037-1044).
 
     reuse=True (default whenever every window is aligned to the token grid, as the reference's
     (20,40,40)/(10,20,20) sweep is): Engine.forward_occluded — the patch embedding and every spatial-transformer
@@ -135,8 +139,11 @@ def occlusion_scores(engine: Engine, volume: torch.Tensor, text_latents: torch.T
     reuse=False: dense path, the cube is applied inside the patch-embedding load of a full forward."""
     dev = engine.dev
     cfg = engine.cfg
-    tl = text_latents[:1]
-    scores = torch.empty(len(windows), device=dev)
+    tl = text_latents if all_prompts else text_latents[:1]
+    scores = torch.empty(len(windows), tl.shape[0], device=dev)
+
+    def result(orig):
+        return (orig[0].clone(), scores) if all_prompts else (float(orig[0, 0]), scores[:, 0])
     tp, ps = cfg.temporal_patch_size, cfg.patch_size
     aligned = (patch_size[0] % tp == 0 and patch_size[1] % ps == 0 and patch_size[2] % ps == 0 and
                all(d % tp == 0 and h % ps == 0 and w % ps == 0 for (d, h, w) in windows))
@@ -146,21 +153,20 @@ def occlusion_scores(engine: Engine, volume: torch.Tensor, text_latents: torch.T
         if not aligned:
             raise ValueError("occlusion reuse needs windows aligned to the token grid")
         cache = engine.occlusion_baseline(volume, tl, fill)
-        orig = cache.sim[0, 0]
         cubes = np.array([[d // tp, h // ps, w // ps] for (d, h, w) in windows], dtype=np.int64).reshape(-1, 3)
         shape = (patch_size[0] // tp, patch_size[1] // ps, patch_size[2] // ps)
         for s in range(0, len(windows), reuse_batch):
             e = min(s + reuse_batch, len(windows))
-            scores[s:e] = engine.forward_occluded(cache, cubes[s:e], shape, tl).sim[:, 0]
-        return float(orig), scores
-    orig = engine.forward(volume, tl).sim[0, 0]
+            scores[s:e] = engine.forward_occluded(cache, cubes[s:e], shape, tl).sim
+        return result(cache.sim)
+    orig = engine.forward(volume, tl).sim
     wins = torch.tensor([[d, h, w, patch_size[0], patch_size[1], patch_size[2]] for (d, h, w) in windows],
                         dtype=torch.int32, device=dev).reshape(-1, 6)
     for s in range(0, len(windows), batch):
         e = min(s + batch, len(windows))
         ctx = engine.forward(volume, tl, batch=e - s, occl=wins[s:e].contiguous(), occl_value=fill)
-        scores[s:e] = ctx.sim[:, 0]
-    return float(orig), scores
+        scores[s:e] = ctx.sim
+    return result(orig)
 
 
 def occlusion_heatmap(orig: float, scores: torch.Tensor, included: torch.Tensor, shape, patch_size, stride,
@@ -210,6 +216,29 @@ def occlusion_sensitivity(engine: Engine, volume: torch.Tensor, text_latents: to
     scores, included = combine_sharded(local, start, end, len(windows))
     heat = occlusion_heatmap(orig, scores, included, (D, H, W), patch_size, stride, threshold, rot90)
     return heat, {"orig": orig, "scores": scores, "included": included, "windows": windows}
+
+
+def occlusion_sensitivity_multi(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor,
+                                patch_size=(20, 40, 40), stride=(10, 20, 20), batch: int = 8,
+                                parity_sharding: bool = True, threshold: float = 0.0, rot90: bool = True,
+                                reuse: Optional[bool] = None):
+    """One occlusion sweep shared by all P prompts of text_latents [P, NL]: the reference re-runs the whole sweep
+    for every positive pathology (visualizations.py:1037-1044) although only the final dot product depends on the
+    prompt.  Returns ([P heat maps], aux); each heat map equals occlusion_sensitivity() with that prompt alone."""
+    rank, world = _world()
+    D, H, W = volume.shape[-3:]
+    windows = occlusion_windows((D, H, W), patch_size, stride)
+    start, end = shard_range(len(windows), rank, world, parity_sharding)
+    orig, local = occlusion_scores(engine, volume, text_latents, windows[start:end], patch_size, batch, reuse=reuse,
+                                   all_prompts=True)
+    P = text_latents.shape[0]
+    heats, all_scores, included = [], [], None
+    for j in range(P):
+        sc, included = combine_sharded(local[:, j].contiguous(), start, end, len(windows))
+        all_scores.append(sc)
+        heats.append(occlusion_heatmap(float(orig[j]), sc, included, (D, H, W), patch_size, stride, threshold, rot90))
+    return heats, {"orig": orig, "scores": torch.stack(all_scores, 1) if P else None, "included": included,
+                   "windows": windows}
 
 
 # ------------------------------------------------------------------------------------------- integrated gradients
@@ -468,9 +497,16 @@ class Visualizations:
             tens = {k: torch.tensor(v, dtype=torch.float32, device=self.accelerator.device).unsqueeze(0)
                     for k, v in emb.items()}
             pos = (labels == 1).nonzero(as_tuple=True)[0]
-            for name in [PATHOLOGIES[i] for i in pos.tolist()]:
-                self.maybe_print("Processing pathology:", name)
-                heatmaps[name] = self._compute_occlusion(image, text_tokens, tens[name], patch_size, stride, threshold)
+            names = [PATHOLOGIES[i] for i in pos.tolist()]
+            if names:
+                # one sweep for all positive pathologies (the reference runs one sweep each, :1037-1044)
+                self.maybe_print("Processing pathologies:", ", ".join(names))
+                tl = self._text_latents(text_tokens, torch.cat([tens[n] for n in names], dim=0))
+                heats, aux = occlusion_sensitivity_multi(self._engine(), image.float().contiguous(), tl, patch_size,
+                                                         stride, self.window_batch, self.parity_sharding, threshold)
+                self.saved_outputs["occlusion"] = aux
+                for n, hm in zip(names, heats):
+                    heatmaps[n] = hm.cpu().numpy() if self.accelerator.is_main_process else None
         else:
             heatmap = self._compute_occlusion(image, text_tokens, None, patch_size, stride, threshold)
         if self.accelerator.is_main_process:

@@ -144,6 +144,23 @@ def test_occlusion_reuse_equals_dense_forward(setup):
     assert torch.equal(ctx_f.x_pre_vq, ctx_d.x_pre_vq)
 
 
+def test_occlusion_multi_prompt_sweep_equals_single_prompt_sweeps(setup):
+    """One sweep scoring P prompts == P independent sweeps (the reference's loop over positive
+    pathologies, visualizations.py:1037-1044): bit-identical scores and heat maps."""
+    from ctclip_b200 import attribution as A
+    eng, vol, _, _, _ = setup
+    emb = torch.randn(3, 768, generator=torch.Generator().manual_seed(11)).to(DEV)
+    tl = eng.text_latents(emb)
+    ps = st = (120, 240, 240)
+    heats, aux = A.occlusion_sensitivity_multi(eng, vol, tl, ps, st)
+    assert len(heats) == 3 and tuple(aux["scores"].shape) == (8, 3)
+    for j in range(3):
+        h1, a1 = A.occlusion_sensitivity(eng, vol, tl[j:j + 1].contiguous(), ps, st)
+        assert a1["orig"] == float(aux["orig"][j])
+        assert torch.equal(a1["scores"], aux["scores"][:, j])
+        assert torch.equal(h1, heats[j])
+
+
 def test_occlusion_heatmap_default_grid_vs_oracle():
     """12 167-window grid, random scores, shard with dropped remainder: bit-exact masks / counts."""
     from ctclip_b200 import attribution as A

@@ -216,7 +216,8 @@ def _attn_ref(q, kv, qs, ks, scale, bias, B, T, H, W, heads, mode):
 
 
 @pytest.mark.parametrize("mode,B,T,H,W,heads", [(0, 1, 2, 24, 24, 8), (1, 1, 24, 24, 24, 8), (0, 2, 6, 6, 6, 2),
-                                                (1, 2, 6, 6, 6, 2), (0, 1, 1, 10, 10, 4)])
+                                                (1, 2, 6, 6, 6, 2), (0, 1, 1, 10, 10, 4), (0, 1, 3, 8, 8, 2),
+                                                (0, 2, 1, 16, 8, 1)])
 def test_attention_fwd_bwd_probs(lib, mode, B, T, H, W, heads):
     if mode == 1 and not (T == H == W):
         pytest.skip("temporal mode uses T tokens")
