@@ -17,6 +17,8 @@
 // Backward (input gradients only) recomputes P from the saved row log-sum-exp:
 //   kernel dQ  : per 64-query block  — dP = dO V^T, dS = P∘(dP − D), dQ^ = dS K^, l2norm/scale adjoint
 //   kernel dKV : per 64-key block    — the transposed problem for dV = P^T dO, dK^ = dS^T Q^
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ctc_internal.h"
 
@@ -34,7 +36,7 @@ static constexpr float LN2 = 0.6931471805599453f;
 // resident CTAs per SM the register allocation must allow: small CTAs (temporal sequences) rely on several
 // independent CTAs per SM to overlap their load / compute phases
 constexpr int attn_min_blocks(int threads, int two_block_limit) {
-    return threads <= 128 ? 4 : (threads <= two_block_limit ? 2 : 1);
+    return threads <= 64 ? 8 : (threads <= 128 ? 4 : (threads <= two_block_limit ? 2 : 1));
 }
 
 struct AttnParams {
@@ -670,7 +672,17 @@ static int launch_attn(const AttnParams& p, dim3 grid, int threads, size_t smem,
     return 0;
 }
 
-// small-sequence configuration (temporal, n <= 32): all heads of a sequence in one CTA when heads % 8 == 0
+// small-sequence configuration (temporal, n <= 32): HPC heads of a sequence per CTA
+static int small_hpc(int heads) {
+    static int pref = -1;
+    if (pref < 0) {
+        const char* e = getenv("CTC_ATTN_SMALL_HPC");
+        pref = e ? atoi(e) : 2;
+    }
+    int h = pref;
+    while (h > 1 && heads % h != 0) h >>= 1;
+    return h < 1 ? 1 : h;
+}
 static bool use_small(const AttnParams& p) { return p.n <= 32 && p.bias_table == nullptr; }
 
 // Row blocks of one (sequence, head) are walked by ONE CTA (gridDim.z = 1, resident K/V or Q/dO loaded and
@@ -728,7 +740,10 @@ extern "C" int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, cons
     p.ldkv = ldkv; p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale;
     p.out = (__nv_bfloat16*)o; p.lse = lse;
     cudaStream_t st = (cudaStream_t)stream;
-    if (small) return (heads % 2 == 0) ? run_fwd<32, 32, 2, false>(p, st) : run_fwd<32, 32, 1, false>(p, st);
+    if (small) {
+        const int h = small_hpc(heads);
+        return h >= 8 ? run_fwd<32, 32, 8, false>(p, st) : h >= 2 ? run_fwd<32, 32, 2, false>(p, st) : run_fwd<32, 32, 1, false>(p, st);
+    }
     return (p.n > 128) ? run_fwd<192, 64, 1, false>(p, st) : run_fwd<64, 64, 1, false>(p, st);
 }
 
@@ -744,7 +759,10 @@ extern "C" int ctc_attention_probs(const void* q, int64_t ldq, const void* k, in
     p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale;
     p.lse = const_cast<float*>(lse); p.probs = probs;
     cudaStream_t st = (cudaStream_t)stream;
-    if (small) return (heads % 2 == 0) ? run_fwd<32, 32, 2, true>(p, st) : run_fwd<32, 32, 1, true>(p, st);
+    if (small) {
+        const int h = small_hpc(heads);
+        return h >= 8 ? run_fwd<32, 32, 8, true>(p, st) : h >= 2 ? run_fwd<32, 32, 2, true>(p, st) : run_fwd<32, 32, 1, true>(p, st);
+    }
     return (p.n > 128) ? run_fwd<192, 64, 1, true>(p, st) : run_fwd<64, 64, 1, true>(p, st);
 }
 
@@ -764,6 +782,9 @@ extern "C" int ctc_attention_bwd(const void* q, int64_t ldq, const void* k, cons
     p.lse = const_cast<float*>(lse); p.delta = delta_ws;
     p.dq = (__nv_bfloat16*)dq; p.lddq = lddq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddkv = lddkv;
     cudaStream_t st = (cudaStream_t)stream;
-    if (small) return (heads % 2 == 0) ? run_bwd<32, 32, 2>(p, st) : run_bwd<32, 32, 1>(p, st);
+    if (small) {
+        const int h = small_hpc(heads);
+        return h >= 8 ? run_bwd<32, 32, 8>(p, st) : h >= 2 ? run_bwd<32, 32, 2>(p, st) : run_bwd<32, 32, 1>(p, st);
+    }
     return (p.n > 128) ? run_bwd<96, 64, 1>(p, st) : run_bwd<64, 64, 1>(p, st);
 }

@@ -15,6 +15,8 @@
 //
 // A plain SIMT kernel with the same epilogues (gemm_simt) is kept as a bring-up / cross-check
 // comparator for tests; the product path always uses the tcgen05 kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ctc_internal.h"
 
@@ -579,7 +581,9 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
         return 0;
     }
     // tile width: 128x256 tiles unless N only divides by 128 (e.g. the padded FF inner dim 1408)
-    const bool bn256 = (epi == CTC_EPI_ARGMAX) || (N % 256 == 0) || (N % 128 != 0);
+    static int force256 = -1;      // tuning knob: CTC_GEMM_BN256=1 uses 128x256 tiles even when N % 256 == 128
+    if (force256 < 0) { const char* e = getenv("CTC_GEMM_BN256"); force256 = e ? atoi(e) : 0; }
+    const bool bn256 = (epi == CTC_EPI_ARGMAX) || (N % 256 == 0) || (N % 128 != 0) || (force256 && N >= 512);
     const int BNsel = bn256 ? 256 : 128;
     g.n_tiles_n = (N + BNsel - 1) / BNsel;
     CUtensorMap ta, tb;

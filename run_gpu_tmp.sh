@@ -1,5 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | grep -v Warning | tail -n 30 > gpurun_out/r17_tests.log
-timeout 600 python tools/time_engine.py 8 > gpurun_out/r17_time_b8.log 2>&1
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r17_bench.json 2> gpurun_out/r17_bench.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r20_bench2.json 2> gpurun_out/r20_bench2.err
 echo done

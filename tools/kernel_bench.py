@@ -1,0 +1,70 @@
+"""Micro-benchmarks of single kernels at the batch-8 shapes of the step (CUDA events, L2 flushed between
+iterations by cycling through more buffers than fit the 126 MB L2).  Development aid.
+    python tools/kernel_bench.py [gemm|attn_t|attn_s|all]"""
+import sys, os
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "ct-clip-ut_b200"))
+import torch
+from ctclip_b200 import _lib as L
+
+dev = torch.device("cuda")
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+B, T, H, W, heads = 8, 24, 24, 24, 8
+R = B * T * H * W
+bf = torch.bfloat16
+
+
+def timeit(fn, n=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3   # us
+
+
+def rnd(*shape, dtype=torch.float32, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).to(dtype)
+
+
+if what in ("gemm", "all"):
+    print(f"env CTC_GEMM_BN256={os.environ.get('CTC_GEMM_BN256', '0')}")
+    for name, N, K, epi, resid in [("q", 256, 512, L.EPI_BF16, False), ("kv", 512, 512, L.EPI_BF16, False),
+                                   ("out+res", 512, 256, L.EPI_F32, True), ("ff1 geglu (no u)", 2816, 512, L.EPI_GEGLU, False),
+                                   ("ff2+res", 512, 1408, L.EPI_F32, True), ("dh", 1408, 512, L.EPI_BF16, False),
+                                   ("dxn2", 512, 2816, L.EPI_F32, False), ("pe", 512, 4000, L.EPI_F32, False),
+                                   ("pe bwd", 4000, 512, L.EPI_BF16, False)]:
+        a = rnd(R, K, dtype=bf)
+        w = rnd(N, K, dtype=bf, scale=K ** -0.5)
+        if epi == L.EPI_GEGLU:
+            out = torch.empty(R, N // 2, device=dev, dtype=bf)
+        else:
+            out = torch.empty(R, N, device=dev, dtype=bf if epi == L.EPI_BF16 else torch.float32)
+        res = rnd(R, N) if resid else None
+        def f():
+            L.call("ctc_gemm_bf16", a, K, w, K, out, out.stride(0), R, N, K, epi, None, res, N if resid else 0, None, 0, 0,
+                   L.stream_ptr())
+        us = timeit(f)
+        print(f"  gemm {name:18s} N={N:5d} K={K:5d}: {us:8.1f} us  {2.0 * R * N * K / us / 1e6:8.1f} TFLOP/s")
+
+for mode, tag in ((1, "attn_t"), (0, "attn_s")):
+    if what not in (tag, "all"):
+        continue
+    print(f"env CTC_ATTN_SMALL_HPC={os.environ.get('CTC_ATTN_SMALL_HPC', '2')}")
+    inner = heads * 32
+    q, kv = rnd(R, inner, dtype=bf), rnd(R, 2 * inner, dtype=bf)
+    qs, ks = torch.ones(32, device=dev), torch.ones(32, device=dev)
+    table = rnd(heads, 47 * 47, scale=0.5) if mode == 0 else None
+    o = torch.empty(R, inner, device=dev, dtype=bf)
+    lse = torch.empty(R, heads, device=dev)
+    d_o = rnd(R, inner, dtype=bf)
+    dq, dkv, delta = torch.empty_like(q), torch.empty_like(kv), torch.empty(R, heads, device=dev)
+    def fwd():
+        L.call("ctc_attention_fwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, heads, qs, ks, 8.0,
+               table, mode, o, lse, L.stream_ptr())
+    def bwd():
+        L.call("ctc_attention_bwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, o, d_o, lse, B, T, H, W, heads,
+               qs, ks, 8.0, table, mode, dq, inner, dkv, dkv.data_ptr() + inner * 2, 2 * inner, delta, L.stream_ptr())
+    print(f"  {tag} fwd {timeit(fwd):8.1f} us   bwd (dq + dkv) {timeit(bwd):8.1f} us")
