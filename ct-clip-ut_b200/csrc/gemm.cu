@@ -580,10 +580,10 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
         CTC_LAUNCH_CHECK();
         return 0;
     }
-    // tile width: 128x256 tiles unless N only divides by 128 (e.g. the padded FF inner dim 1408)
-    static int force256 = -1;      // tuning knob: CTC_GEMM_BN256=1 uses 128x256 tiles even when N % 256 == 128
-    if (force256 < 0) { const char* e = getenv("CTC_GEMM_BN256"); force256 = e ? atoi(e) : 0; }
-    const bool bn256 = (epi == CTC_EPI_ARGMAX) || (N % 256 == 0) || (N % 128 != 0) || (force256 && N >= 512);
+    // tile width: 128x256 tiles; 128x128 only for narrow outputs (N < 512) that divide by 128 but not by 256.
+    // (N = 1408, the padded FF inner dim: 256-wide tiles with a half-empty last tile measured 158 us against
+    // 191 us for 128-wide tiles - twice the MMA work per byte staged through shared memory.)
+    const bool bn256 = (epi == CTC_EPI_ARGMAX) || (N % 256 == 0) || (N % 128 != 0) || (N >= 512);
     const int BNsel = bn256 ? 256 : 128;
     g.n_tiles_n = (N + BNsel - 1) / BNsel;
     CUtensorMap ta, tb;

@@ -176,6 +176,89 @@ latent_proj_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __rest
     }
 }
 
+// Tensor-core version (NL % 64 == 0, L % 64 == 0): the SIMT kernel above stages the pooled chunk in shared memory
+// and is bound by its LDS traffic (1.23 ms for 32 rows, 4 weight passes).  Here each CTA streams its [NL x 1024]
+// weight chunk from HBM ONCE for up to 32 batch rows with mma.sync m16n8k16: the reduction index inside a 32-wide
+// k-block is permuted (thread t owns k = 8t .. 8t+7 of both operands), so that the weight fragment is ONE 16-byte
+// global load per lane and the pooled fragment two float4 loads - no shared memory, no ldmatrix.  The fp32 pooled
+// row is split into bf16 hi + lo parts (two MMAs), which keeps ~16 mantissa bits of the activations; the weights
+// are bf16 as before.  Partials go to partial[chunk, b, n] and are reduced by latent_reduce_kernel (deterministic).
+template <int MT>
+__global__ void __launch_bounds__(256, 1)
+latent_proj_mma_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __restrict__ wv, int B, long long L, int NL,
+                       float* __restrict__ partial) {
+    const int chunk = blockIdx.x;
+    const int b0 = blockIdx.y * (16 * MT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const long long l0 = (long long)chunk * LAT_CH;
+    const int len = (int)min((long long)LAT_CH, L - l0);             // multiple of 64
+    for (int nbase = 0; nbase < NL; nbase += 512) {
+        const int n_w = nbase + warp * 64;                             // this warp's 8 n-tiles: n_w + 8 i + g
+        if (n_w >= NL) continue;
+        float acc[MT][8][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[m][i][0] = acc[m][i][1] = acc[m][i][2] = acc[m][i][3] = 0.f;
+        for (int kb = 0; kb < len; kb += 32) {
+            // weight fragments of the 8 n-tiles: 8 independent 16-byte loads in flight per lane
+            uint4 wf[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                wf[i] = *reinterpret_cast<const uint4*>(wv + (long long)(n_w + 8 * i + g) * L + l0 + kb + 8 * t);
+            // pooled fragments (rows g, g+8 of each m-tile), split into bf16 hi / lo
+            uint32_t ah[MT][2][4], al[MT][2][4];                      // [m-tile][k-step j][a0..a3]
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int row = b0 + 16 * m + g + 8 * r;
+                    float x[8];
+                    if (row < B) {
+                        const float4 p0 = *reinterpret_cast<const float4*>(pooled + (long long)row * L + l0 + kb + 8 * t);
+                        const float4 p1 = *reinterpret_cast<const float4*>(pooled + (long long)row * L + l0 + kb + 8 * t + 4);
+                        x[0] = p0.x; x[1] = p0.y; x[2] = p0.z; x[3] = p0.w; x[4] = p1.x; x[5] = p1.y; x[6] = p1.z; x[7] = p1.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) x[e] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {                  // h = 0: logical k 2t,2t+1 ; h = 1: 2t+8,2t+9
+                            const float u = x[4 * j + 2 * h], v = x[4 * j + 2 * h + 1];
+                            const __nv_bfloat16 uh = __float2bfloat16(u), vh = __float2bfloat16(v);
+                            ah[m][j][r + 2 * h] = pack_bf16(__bfloat162float(uh), __bfloat162float(vh));
+                            al[m][j][r + 2 * h] = pack_bf16(u - __bfloat162float(uh), v - __bfloat162float(vh));
+                        }
+                }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t wr[4] = {wf[i].x, wf[i].y, wf[i].z, wf[i].w};
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        mma_bf16_16816(acc[m][i], ah[m][j], wr[2 * j], wr[2 * j + 1]);
+                        mma_bf16_16816(acc[m][i], al[m][j], wr[2 * j], wr[2 * j + 1]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = b0 + 16 * m + g + 8 * r;
+                if (row >= B) continue;
+                float* o = partial + ((long long)chunk * B + row) * NL + n_w + 2 * t;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float2*>(o + 8 * i) = make_float2(acc[m][i][2 * r], acc[m][i][2 * r + 1]);
+            }
+    }
+}
+
 __global__ void latent_reduce_kernel(const float* __restrict__ partial, int n_chunks, int total, float* __restrict__ latent) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -363,8 +446,18 @@ extern "C" int ctc_latent_proj(const float* pooled, const void* wv_bf16, int B, 
     const int need = (int)((L + LAT_CH - 1) / LAT_CH);
     CTC_REQUIRE(n_chunks == need, "latent_proj: partial buffer must have %d chunks (got %d)", need, n_chunks);
     CTC_REQUIRE(L % 8 == 0, "latent_proj: L=%lld must be a multiple of 8", (long long)L);
-    dim3 grid(n_chunks, (B + LAT_BMAX - 1) / LAT_BMAX);
-    latent_proj_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pooled, (const __nv_bfloat16*)wv_bf16, B, L, NL, partial);
+    const bool mma_ok = NL % 64 == 0 && L % 64 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(wv_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial) & 7) == 0;
+    if (mma_ok && B > 16) {
+        latent_proj_mma_kernel<2><<<dim3(n_chunks, (B + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+            pooled, (const __nv_bfloat16*)wv_bf16, B, L, NL, partial);
+    } else if (mma_ok) {
+        latent_proj_mma_kernel<1><<<dim3(n_chunks, 1), 256, 0, (cudaStream_t)stream>>>(
+            pooled, (const __nv_bfloat16*)wv_bf16, B, L, NL, partial);
+    } else {
+        dim3 grid(n_chunks, (B + LAT_BMAX - 1) / LAT_BMAX);
+        latent_proj_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pooled, (const __nv_bfloat16*)wv_bf16, B, L, NL, partial);
+    }
     CTC_LAUNCH_CHECK();
     const int total = B * NL;
     latent_reduce_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, n_chunks, total, latent);

@@ -1,3 +1,6 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r20_bench2.json 2> gpurun_out/r20_bench2.err
+timeout 900 python -m pytest tests/test_gpu_ops.py -q -m gpu -x -k "latent or gemm" 2>&1 | grep -v Warning | tail -n 8 > gpurun_out/r22_ops.log
+timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_attribution.py -q -m gpu -x 2>&1 | grep -v Warning | tail -n 8 > gpurun_out/r22_model.log
+timeout 600 python tools/time_engine.py 8 > gpurun_out/r22_time_b8.log 2>&1
+timeout 600 python tools/time_occlusion.py 32 > gpurun_out/r22_occ.log 2>&1
 echo done

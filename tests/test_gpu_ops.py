@@ -410,7 +410,8 @@ def test_vq_argmax_gather_bwd(lib):
     assert relerr(dx, dx_ref) < 1e-4
 
 
-@pytest.mark.parametrize("B,L,NL,Bt", [(1, 294912, 512, 1), (11, 2304, 32, 3)])
+@pytest.mark.parametrize("B,L,NL,Bt", [(1, 294912, 512, 1), (11, 2304, 32, 3), (20, 8192, 512, 2), (32, 4160, 128, 1),
+                                       (37, 2048, 576, 1)])
 def test_latent_proj_sim(lib, B, L, NL, Bt):
     pooled = rnd(B, L, seed=1)
     wv = rnd(NL, L, seed=2, scale=1 / math.sqrt(L), dtype=torch.bfloat16)
