@@ -351,12 +351,14 @@ attn_fwd_kernel(const AttnParams p) {
 // adjoint of x^ = l2norm(x) * vec for one row held in mma C layout (quad of lanes owns the row):
 // g = gradient w.r.t. x^ (before the vec factor is applied here).  Returns dx for the 8 elements this
 // thread owns (cols a*8 + 2t, +1 for a = 0..3).
+// Contains full-mask shuffles: EVERY lane of the warp must call it (pass xrow = nullptr for rows outside the
+// sequence; their result is garbage and must not be stored).
 CTC_DEVINL void l2norm_adjoint_row(const __nv_bfloat16* xrow, const float* vec, int t, float (&g)[8], float (&dx)[8]) {
     float x[8];
     float ss = 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(xrow + a * 8 + 2 * t));
+        const float2 v = xrow ? unpack_bf16(*reinterpret_cast<const uint32_t*>(xrow + a * 8 + 2 * t)) : make_float2(0.f, 0.f);
         x[a * 2] = v.x; x[a * 2 + 1] = v.y;
         ss += v.x * v.x + v.y * v.y;
     }
@@ -483,16 +485,18 @@ attn_bwd_dq_kernel(const AttnParams p) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int i = half ? i1 : i0;
-        if (i >= p.n) continue;
-        const long long r = seq_row(p, s, i);
+        const bool ok = i < p.n;                       // no early-out: the adjoint shuffles need the whole warp
+        const long long r = seq_row(p, s, ok ? i : 0);
         float gq[8], dx[8];
 #pragma unroll
         for (int a = 0; a < 4; ++a) { gq[a * 2] = dq[a][half * 2] * p.scale; gq[a * 2 + 1] = dq[a][half * 2 + 1] * p.scale; }
-        l2norm_adjoint_row(p.q + r * p.ldq + head * DH, sv, t, gq, dx);
+        l2norm_adjoint_row(ok ? p.q + r * p.ldq + head * DH : nullptr, sv, t, gq, dx);
         __nv_bfloat16* drow = p.dq + r * p.lddq + head * DH;
+        if (ok) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-            *reinterpret_cast<uint32_t*>(drow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+            for (int a = 0; a < 4; ++a)
+                *reinterpret_cast<uint32_t*>(drow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+        }
     }
   }
 }
@@ -625,21 +629,25 @@ attn_bwd_dkv_kernel(const AttnParams p) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int j = half ? j1 : j0;
-        if (j >= p.n) continue;
-        const long long r = seq_row(p, s, j);
+        const bool ok = j < p.n;                       // no early-out: the adjoint shuffles need the whole warp
+        const long long r = seq_row(p, s, ok ? j : 0);
         __nv_bfloat16* dvrow = p.dv + r * p.lddkv + head * DH;
+        if (ok) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-            *reinterpret_cast<uint32_t*>(dvrow + a * 8 + 2 * t) = pack_bf16(dv[a][half * 2], dv[a][half * 2 + 1]);
+            for (int a = 0; a < 4; ++a)
+                *reinterpret_cast<uint32_t*>(dvrow + a * 8 + 2 * t) = pack_bf16(dv[a][half * 2], dv[a][half * 2 + 1]);
+        }
         // dk^ accumulated against q^ * scale * log2e  ->  undo log2e; k_scale applied inside the adjoint
         float gk[8], dx[8];
 #pragma unroll
         for (int a = 0; a < 4; ++a) { gk[a * 2] = dk[a][half * 2] * LN2; gk[a * 2 + 1] = dk[a][half * 2 + 1] * LN2; }
-        l2norm_adjoint_row(p.k + r * p.ldkv + head * DH, sv + 32, t, gk, dx);
+        l2norm_adjoint_row(ok ? p.k + r * p.ldkv + head * DH : nullptr, sv + 32, t, gk, dx);
         __nv_bfloat16* dkrow = p.dk + r * p.lddkv + head * DH;
+        if (ok) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-            *reinterpret_cast<uint32_t*>(dkrow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+            for (int a = 0; a < 4; ++a)
+                *reinterpret_cast<uint32_t*>(dkrow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+        }
     }
   }
 }
@@ -911,16 +919,18 @@ attn_small_bwd_kernel(const AttnParams p) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int i = half ? i1 : i0;
-                if (i >= p.n) continue;
-                const long long r = seq_row(p, s, i);
+                const bool ok = i < p.n;               // no early-out: the adjoint shuffles need the whole warp
+                const long long r = seq_row(p, s, ok ? i : 0);
                 float gq[8], dx[8];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) { gq[a * 2] = dq[a][half * 2] * p.scale; gq[a * 2 + 1] = dq[a][half * 2 + 1] * p.scale; }
-                l2norm_adjoint_row(p.q + r * p.ldq + head * DH, sv, t, gq, dx);
+                l2norm_adjoint_row(ok ? p.q + r * p.ldq + head * DH : nullptr, sv, t, gq, dx);
                 __nv_bfloat16* drow = p.dq + r * p.lddq + head * DH;
+                if (ok) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    *reinterpret_cast<uint32_t*>(drow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+                    for (int a = 0; a < 4; ++a)
+                        *reinterpret_cast<uint32_t*>(drow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+                }
             }
         }
         // ---- dK, dV: rows = keys, columns = queries
@@ -964,20 +974,24 @@ attn_small_bwd_kernel(const AttnParams p) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int j = mt * 16 + g + 8 * half;
-                if (j >= p.n) continue;
-                const long long r = seq_row(p, s, j);
+                const bool ok = j < p.n;               // no early-out: the adjoint shuffles need the whole warp
+                const long long r = seq_row(p, s, ok ? j : 0);
                 __nv_bfloat16* dvrow = p.dv + r * p.lddkv + head * DH;
+                if (ok) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    *reinterpret_cast<uint32_t*>(dvrow + a * 8 + 2 * t) = pack_bf16(dv[a][half * 2], dv[a][half * 2 + 1]);
+                    for (int a = 0; a < 4; ++a)
+                        *reinterpret_cast<uint32_t*>(dvrow + a * 8 + 2 * t) = pack_bf16(dv[a][half * 2], dv[a][half * 2 + 1]);
+                }
                 float gk[8], dx[8];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) { gk[a * 2] = dk[a][half * 2] * LN2; gk[a * 2 + 1] = dk[a][half * 2 + 1] * LN2; }
-                l2norm_adjoint_row(p.k + r * p.ldkv + head * DH, sv + 32, t, gk, dx);
+                l2norm_adjoint_row(ok ? p.k + r * p.ldkv + head * DH : nullptr, sv + 32, t, gk, dx);
                 __nv_bfloat16* dkrow = p.dk + r * p.lddkv + head * DH;
+                if (ok) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    *reinterpret_cast<uint32_t*>(dkrow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+                    for (int a = 0; a < 4; ++a)
+                        *reinterpret_cast<uint32_t*>(dkrow + a * 8 + 2 * t) = pack_bf16(dx[a * 2], dx[a * 2 + 1]);
+                }
             }
         }
         __syncwarp();
