@@ -144,28 +144,33 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
     import torch
     from ctclip_b200 import attribution as A
 
-    def once():
+    def once(skip_noop):
         t0 = time.perf_counter()
         vol = host_vol.to(dev, non_blocking=True)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
-        heat, aux = A.occlusion_sensitivity(eng, vol, tl)
+        heat, aux = A.occlusion_sensitivity(eng, vol, tl, skip_noop=skip_noop)
         e[1].record()
         ig, _ = A.integrated_gradients(eng, vol, tl, steps=50, batch=5)
         e[2].record()
         out = (heat.cpu(), ig.cpu())
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        return wall, e[0].elapsed_time(e[1]) / 1e3, e[1].elapsed_time(e[2]) / 1e3, int(aux["included"].sum()), out
+        return (wall, e[0].elapsed_time(e[1]) / 1e3, e[1].elapsed_time(e[2]) / 1e3, int(aux["included"].sum()), out,
+                aux["stats"])
 
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    wall, occ_s, ig_s, n_win, _ = once()
-    t = torch.tensor([wall, occ_s, ig_s], device=dev)
+    # headline: EVERY window of the sweep is evaluated.  Second pass: windows that lie entirely in -1 air / padding
+    # (no-ops, score == baseline bit for bit) are detected on the device and skipped - reported separately.
+    wall, occ_s, ig_s, n_win, maps, _ = once(False)
+    wall2, occ2_s, _, _, maps2, stats = once(True)
+    same = bool(torch.equal(maps[0], maps2[0]))
+    t = torch.tensor([wall, occ_s, ig_s, wall2, occ2_s], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall, occ_s, ig_s = (float(v) for v in t)
+    wall, occ_s, ig_s, wall2, occ2_s = (float(v) for v in t)
     dense, execd, _ = occlusion_flops()
     ig_flop = 50 * (FLOP_FWD + FLOP_BWD)
     peak = load_peaks()["tf"] * 1e12 * world
@@ -173,6 +178,9 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
             "seconds_per_volume": wall, "occlusion_s": occ_s, "ig_s": ig_s, "windows": n_win, "ig_steps": 50,
             "h2d_bytes": int(host_vol.numel() * 4), "d2h_bytes": int(2 * host_vol.numel() * 4),
             "occlusion_mode": "frame reuse: patch embedding + unreachable spatial frames from the baseline cache",
+            "with_noop_window_skip": {"seconds_per_volume": wall2, "occlusion_s": occ2_s, "value": 1.0 / wall2,
+                                      "windows_evaluated_rank0": stats.get("evaluated"),
+                                      "windows_noop_rank0": stats.get("noop"), "heat_map_identical": same},
             "dense_equiv_pflop": (dense + ig_flop) / 1e15, "executed_pflop": (execd + ig_flop) / 1e15,
             "frac_of_tensor_peak_executed": (execd + ig_flop) / (occ_s + ig_s) / peak,
             "timing": "wall clock incl. H2D of the volume and D2H of both maps, max over ranks; one un-warmed pass "

@@ -301,7 +301,40 @@ occlusion_heat_kernel(const float* __restrict__ imp, const unsigned char* __rest
 
 }  // namespace ctc
 
+namespace ctc {
+// flags[t, h, w] = 1 iff every voxel of patch (t, h, w) equals `value` (one CTA per patch, 128-bit loads).
+// An occlusion window whose patches are all already filled with the occlusion value leaves the volume
+// unchanged, so its score equals the un-occluded score exactly (visualizations.py:380-390 would compute
+// importance = 0 for it after a full forward).
+__global__ void __launch_bounds__(128)
+patch_is_constant_kernel(const float* __restrict__ vol, int D, int H, int W, int pt, int p, float value,
+                         unsigned char* __restrict__ flags) {
+    const int Wp = W / p, Hp = H / p;
+    const int wp = blockIdx.x % Wp, hp = (blockIdx.x / Wp) % Hp, tp = blockIdx.x / (Wp * Hp);
+    const int q = p >> 2;                                   // float4 per patch row
+    int bad = 0;
+    for (int i = threadIdx.x; i < pt * p * q; i += blockDim.x) {
+        const int c4 = i % q, y = (i / q) % p, d = i / (q * p);
+        const float4 v = *reinterpret_cast<const float4*>(vol + ((long long)(tp * pt + d) * H + hp * p + y) * W + wp * p + c4 * 4);
+        bad |= (v.x != value) | (v.y != value) | (v.z != value) | (v.w != value);
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) flags[blockIdx.x] = bad ? 0 : 1;
+}
+}  // namespace ctc
+
 using namespace ctc;
+
+extern "C" int ctc_patch_is_constant(const float* volume, int D, int H, int W, int pt, int p, float value,
+                                     unsigned char* flags, void* stream) {
+    CTC_REQUIRE(D % pt == 0 && H % p == 0 && W % p == 0 && p % 4 == 0,
+                "patch_is_constant: volume %dx%dx%d / patch %dx%dx%d (p must be a multiple of 4)", D, H, W, pt, p, p);
+    CTC_REQUIRE((reinterpret_cast<uintptr_t>(volume) & 15) == 0, "patch_is_constant: volume not 16-byte aligned");
+    const int n = (D / pt) * (H / p) * (W / p);
+    patch_is_constant_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(volume, D, H, W, pt, p, value, flags);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int ctc_minmax(const float* x, int64_t n, float* mm, void* stream) {
     minmax_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(x, n, mm);

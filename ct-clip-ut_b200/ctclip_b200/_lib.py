@@ -51,7 +51,10 @@ SIGNATURES = {
     "ctc_gradcam": [P, P, P, I, I, P, P],
     "ctc_upsample_trilinear": [P, I, I, I, P, I, I, I, I, P],
     "ctc_ig_combine": [P, P, L, F, P, P, P],
+    "ctc_preprocess_ct": [P, I, I, I, I, L, L, L, F, F, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                          ctypes.c_double, I, I, I, F, P, P, P],
     "ctc_minmax": [P, L, P, P],
+    "ctc_patch_is_constant": [P, I, I, I, I, I, F, P, P],
     "ctc_normalize": [P, I, I, I, P, I, I, P, P],
     "ctc_hist16": [P, L, I, ctypes.c_uint, P, P],
     "ctc_ig_finalize": [P, I, I, I, F, F, F, F, I, P, P],

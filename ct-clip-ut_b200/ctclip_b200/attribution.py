@@ -125,7 +125,8 @@ def quantile_linear(x: torch.Tensor, q: float) -> float:
 # ------------------------------------------------------------------------------------------- occlusion
 def occlusion_scores(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor, windows: Sequence,
                      patch_size, batch: int = 8, fill: float = -1.0, reuse: Optional[bool] = None,
-                     reuse_batch: int = 32, all_prompts: bool = False):
+                     reuse_batch: int = 32, all_prompts: bool = False, skip_noop: bool = True,
+                     stats: Optional[dict] = None):
     """Baseline score and one score per window (visualizations.py:370-388).  Returns (orig, scores fp32
     [len(windows)] on device).  Perturbed volumes are never materialised.
 
@@ -136,7 +137,11 @@ def occlusion_scores(engine: Engine, volume: torch.Tensor, text_latents: torch.T
     reuse=True (default whenever every window is aligned to the token grid, as the reference's
     (20,40,40)/(10,20,20) sweep is): Engine.forward_occluded — the patch embedding and every spatial-transformer
     frame the cube cannot reach come from the cached baseline; same arithmetic, ~40 % fewer executed FLOPs.
-    reuse=False: dense path, the cube is applied inside the patch-embedding load of a full forward."""
+    reuse=False: dense path, the cube is applied inside the patch-embedding load of a full forward.
+    skip_noop (reuse path only): a window whose patches are ALL already filled with `fill` (air / padding, exactly
+    -1 after preprocess.py:135-147) leaves the volume unchanged, so its score is the baseline score bit for bit;
+    such windows are detected on the device (ctc_patch_is_constant) and not evaluated.  `stats` receives
+    {"evaluated", "noop"} counts."""
     dev = engine.dev
     cfg = engine.cfg
     tl = text_latents if all_prompts else text_latents[:1]
@@ -155,9 +160,29 @@ def occlusion_scores(engine: Engine, volume: torch.Tensor, text_latents: torch.T
         cache = engine.occlusion_baseline(volume, tl, fill)
         cubes = np.array([[d // tp, h // ps, w // ps] for (d, h, w) in windows], dtype=np.int64).reshape(-1, 3)
         shape = (patch_size[0] // tp, patch_size[1] // ps, patch_size[2] // ps)
-        for s in range(0, len(windows), reuse_batch):
-            e = min(s + reuse_batch, len(windows))
-            scores[s:e] = engine.forward_occluded(cache, cubes[s:e], shape, tl).sim
+        todo = np.arange(len(windows))
+        if skip_noop and len(windows):
+            D, H, W = volume.shape[-3:]
+            flags = torch.empty(D // tp, H // ps, W // ps, dtype=torch.uint8, device=dev)
+            call("ctc_patch_is_constant", volume, D, H, W, tp, ps, float(fill), flags, stream_ptr())
+            f = flags.cpu().numpy().astype(bool)
+            noop = np.ones(len(windows), dtype=bool)
+            for a in range(shape[0]):
+                for b in range(shape[1]):
+                    for c in range(shape[2]):
+                        noop &= f[cubes[:, 0] + a, cubes[:, 1] + b, cubes[:, 2] + c]
+            todo = np.nonzero(~noop)[0]
+            if noop.any():
+                scores[torch.from_numpy(np.nonzero(noop)[0]).to(dev)] = cache.sim[0]
+        if stats is not None:
+            stats.update(evaluated=int(len(todo)), noop=int(len(windows) - len(todo)))
+        for s in range(0, len(todo), reuse_batch):
+            sel = todo[s:s + reuse_batch]
+            sim = engine.forward_occluded(cache, cubes[sel], shape, tl).sim
+            if len(sel) == sel[-1] - sel[0] + 1:
+                scores[sel[0]:sel[-1] + 1] = sim
+            else:
+                scores[torch.from_numpy(sel).to(dev)] = sim
         return result(cache.sim)
     orig = engine.forward(volume, tl).sim
     wins = torch.tensor([[d, h, w, patch_size[0], patch_size[1], patch_size[2]] for (d, h, w) in windows],
@@ -205,17 +230,20 @@ def combine_sharded(local: torch.Tensor, start: int, end: int, total: int) -> Tu
 
 def occlusion_sensitivity(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor,
                           patch_size=(20, 40, 40), stride=(10, 20, 20), batch: int = 8, parity_sharding: bool = True,
-                          threshold: float = 0.0, rot90: bool = True, reuse: Optional[bool] = None):
+                          threshold: float = 0.0, rot90: bool = True, reuse: Optional[bool] = None,
+                          skip_noop: bool = True):
     """_compute_occlusion (visualizations.py:335-424), sharded over the ranks of the default process group.
     Cross-rank exchange: ONE all-gather of per-window scores (<= 49 KB) instead of two 221 MB reduces."""
     rank, world = _world()
     D, H, W = volume.shape[-3:]
     windows = occlusion_windows((D, H, W), patch_size, stride)
     start, end = shard_range(len(windows), rank, world, parity_sharding)
-    orig, local = occlusion_scores(engine, volume, text_latents, windows[start:end], patch_size, batch, reuse=reuse)
+    stats: dict = {}
+    orig, local = occlusion_scores(engine, volume, text_latents, windows[start:end], patch_size, batch, reuse=reuse,
+                                   skip_noop=skip_noop, stats=stats)
     scores, included = combine_sharded(local, start, end, len(windows))
     heat = occlusion_heatmap(orig, scores, included, (D, H, W), patch_size, stride, threshold, rot90)
-    return heat, {"orig": orig, "scores": scores, "included": included, "windows": windows}
+    return heat, {"orig": orig, "scores": scores, "included": included, "windows": windows, "stats": stats}
 
 
 def occlusion_sensitivity_multi(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor,

@@ -131,9 +131,16 @@ class Engine:
         self.dev = plan.device
         self.gemm_impl = gemm_impl
         self.fuse_geglu_bwd = False
+        self._row_cap = 0
 
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.float32):
+        """Uninitialised device buffer.  While `_row_cap` is set (occlusion fast path: the number of changed frames
+        varies from batch to batch), 2-D buffers are carved out of a `_row_cap`-row allocation so that the caching
+        allocator sees the same block sizes every batch instead of a fresh cudaMalloc per new shape."""
+        cap = self._row_cap
+        if cap and len(shape) == 2 and shape[0] <= cap:
+            return torch.empty(cap, shape[1], dtype=dtype, device=self.dev)[:shape[0]]
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
     def gemm(self, a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, epi: int, bias=None, resid=None, aux=None):
@@ -348,15 +355,19 @@ class Engine:
             views.append(packed[o:o + n])
             o += n
         # ---- changed input frames: baseline tokens with the cube's rows replaced by the occluded-patch embedding
-        x = self._empty(Wn * nt * HW, C)
-        call("ctc_frames_gather", None, cache.spatial_in[0], views[0], Wn * nt, HW * C, x, stream_ptr())
-        call("ctc_rows_fill", x, views[1], len(rows), C, cache.e_mask, stream_ptr())
-        ctx = Ctx(B=Wn, T=T)
-        for l, lw in enumerate(pl.spatial):
-            x, _ = self._layer_fwd(x, lw, 1, layer_F[l], MODE_SPATIAL, False,
-                                   frames=(cache.spatial_in[l], views[2 + l]))
-        xs_c = self._empty(x.shape[0], C)
-        self.layernorm(x, pl.spatial_norm_g, pl.spatial_norm_b, y_f32=xs_c)
+        self._row_cap = Wn * min(T, nt + 2 * len(pl.spatial)) * HW      # most changed frames a batch can have
+        try:
+            x = self._empty(Wn * nt * HW, C)
+            call("ctc_frames_gather", None, cache.spatial_in[0], views[0], Wn * nt, HW * C, x, stream_ptr())
+            call("ctc_rows_fill", x, views[1], len(rows), C, cache.e_mask, stream_ptr())
+            ctx = Ctx(B=Wn, T=T)
+            for l, lw in enumerate(pl.spatial):
+                x, _ = self._layer_fwd(x, lw, 1, layer_F[l], MODE_SPATIAL, False,
+                                       frames=(cache.spatial_in[l], views[2 + l]))
+            xs_c = self._empty(x.shape[0], C)
+            self.layernorm(x, pl.spatial_norm_g, pl.spatial_norm_b, y_f32=xs_c)
+        finally:
+            self._row_cap = 0
         xs = self._empty(Wn * T * HW, C)
         call("ctc_frames_gather", xs_c, cache.x_s_out, views[-1], Wn * T, HW * C, xs, stream_ptr())
         del x, xs_c

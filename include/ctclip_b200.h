@@ -185,7 +185,21 @@ int ctc_ig_combine(const float* volume, const float* gsum, int64_t n, float inv_
                    void* stream);
 
 /* Global min/max of an fp32 array into mm[2] (caller pre-sets {+inf, -inf}). */
+/* CT preprocessing in front of the patch embedding (src/utils/preprocess.py:84-151, model_type "ctclip"), fused:
+ * HU rescale slope*x+intercept, trilinear resample (align_corners=False) from (z_spacing, xy_spacing, xy_spacing)
+ * to (target_z, target_xy, target_xy), clamp [-1000,1000] / 1000, centre crop / symmetric pad with pad_value to
+ * [D,H,W].  raw: device array of logical shape [H0,W0,D0] (the reference's NIfTI axis order) with element strides
+ * (sH,sW,sD); raw_dtype 0 = float32, 1 = int16, 2 = float64.  out fp32 [D,H,W]; resampled_dhw (host, optional)
+ * receives the intermediate resampled shape. */
+int ctc_preprocess_ct(const void* raw, int raw_dtype, int H0, int W0, int D0, int64_t sH, int64_t sW, int64_t sD,
+                      float slope, float intercept, double z_spacing, double xy_spacing, double target_z,
+                      double target_xy, int D, int H, int W, float pad_value, float* out, int* resampled_dhw,
+                      void* stream);
 int ctc_minmax(const float* x, int64_t n, float* mm, void* stream);
+/* flags uint8 [D/pt, H/p, W/p]: 1 iff every voxel of the patch equals `value`.  An occlusion window made only of
+ * such patches leaves the volume unchanged: its score is the un-occluded score (visualizations.py:380-390). */
+int ctc_patch_is_constant(const float* volume, int D, int H, int W, int pt, int p, float value, unsigned char* flags,
+                          void* stream);
 /* The reference's normalisations: mode 0 (v-min)/(max+1e-8) [raw attention :674, Grad-CAM :946,
  * IG :882]; mode 1 (v-min)/(max-min+1e-8) [rollout :812, occlusion :414]; mode 2 v/(max+1e-8) [IG :893];
  * optional fused np.rot90(k=-1, axes=(1,2)): in [D,H,W] -> out [D,W,H]. */

@@ -130,8 +130,14 @@ def test_occlusion_reuse_equals_dense_forward(setup):
     eng, vol, tl, _, _ = setup
     ps = (20, 40, 40)
     windows = [(0, 0, 0), (220, 440, 440), (100, 200, 220), (210, 0, 440), (10, 20, 20), (150, 440, 0), (220, 0, 0)]
-    o_fast, s_fast = A.occlusion_scores(eng, vol, tl, windows, ps, reuse=True, reuse_batch=4)
+    stats = {}
+    o_fast, s_fast = A.occlusion_scores(eng, vol, tl, windows, ps, reuse=True, reuse_batch=4, stats=stats)
     o_dense, s_dense = A.occlusion_scores(eng, vol, tl, windows, ps, reuse=False, batch=4)
+    # windows lying entirely in the -1 border of the synthetic volume are recognised as no-ops and not evaluated;
+    # evaluating them anyway gives the same bits
+    assert stats == {"evaluated": 2, "noop": 5}, stats
+    _, s_all = A.occlusion_scores(eng, vol, tl, windows, ps, reuse=True, reuse_batch=4, skip_noop=False)
+    assert torch.equal(s_all, s_fast)
     print(f"[occlusion reuse] orig {o_fast:.7f} / {o_dense:.7f}\n  fast  {s_fast.cpu().numpy()}\n  dense {s_dense.cpu().numpy()}")
     assert o_fast == o_dense
     assert float((s_fast - s_dense).abs().max()) < 1e-6
