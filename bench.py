@@ -251,11 +251,16 @@ def run_product(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = os.environ.get("CTC_BENCH_PROFILE_RANGE") == "1"     # ncu --profile-from-start off: timed steps only
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(args.steps):
         graph.replay()
     e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = launches_per_step * args.steps
     ms = e0.elapsed_time(e1)
     if world > 1:

@@ -312,6 +312,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tm = tile / tiles_n, tn = tile % tiles_n;
+            if constexpr (EPI == CTC_EPI_F32) {
+                // While this tile's MMAs run, pull the residual rows this warp will add (32 rows x its columns, fp32)
+                // into L2: the epilogue's loads then hit L2 instead of waiting on HBM with only 4 KB in flight per warp.
+                if (g.resid) {
+                    const int prow = tm * BM + ew * 32 + lane;
+                    const int pcol = tn * BN + cbeg;
+                    if (prow < g.M) {
+                        const float* pr = g.resid + (long long)prow * g.ldr + pcol;
+#pragma unroll
+                        for (int c = 0; c < kColsPerWarp; c += 32)
+                            if (pcol + c < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + c));
+                    }
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int row = tm * BM + ew * 32 + lane;
