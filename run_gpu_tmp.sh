@@ -1,6 +1,7 @@
 cd $GRAFT_REPO_ROOT
-timeout 200 python -m pytest tests/test_gpu_ops.py -q -m gpu -x -k "gemm" 2>&1 | grep -v Warning | tail -n 4 > gpurun_out/r27_ops.log
-timeout 200 python tools/kernel_bench.py gemm > gpurun_out/r27_gemm.log 2>&1
-timeout 200 python tools/time_engine.py 8 > gpurun_out/r27_time_b8.log 2>&1
-timeout 200 python tools/time_occlusion.py 32 > gpurun_out/r27_occ.log 2>&1
+CMD="python bench.py --steps 1 --warmup 3 --no-attribution --no-cpu-baseline"
+timeout 300 $CMD > gpurun_out/r28_plain.json 2> gpurun_out/r28_plain.err || { echo plain failed; exit 1; }
+CTC_BENCH_PROFILE_RANGE=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r28_launches.csv $CMD > gpurun_out/r28_ncu.log 2>&1
+CTC_BENCH_PROFILE_RANGE=1 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_tcgen05 -c 16 -f -o gpurun_out/r28_gemm $CMD > gpurun_out/r28_ncu2.log 2>&1
+CTC_BENCH_PROFILE_RANGE=1 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"attn_|peg_tma|patchify|latent_proj_mma" -c 12 -f -o gpurun_out/r28_misc $CMD > gpurun_out/r28_ncu3.log 2>&1
 echo done
