@@ -28,6 +28,7 @@ UNIT = "volumes/s"
 BATCH = 8
 FLOP_FWD = 789.6e9          # SURVEY §8d, per volume
 FLOP_BWD = 707.7e9          # input-gradient only (no weight gradients: attribution never needs them)
+NCU_GEMM_TRAFFIC_BYTES = 610.7e6   # measured offline with ncu (see roofline.traffic_source); not re-measured per run
 
 
 def load_peaks():
@@ -354,7 +355,10 @@ def run_product(args):
     gemm_ms = sum(s.elapsed_time(e) for _, s, e in events)
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12
     roofline = {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf"],
-                "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": NCU_GEMM_TRAFFIC_BYTES,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the six distinct "
+                                  "forward GEMM shapes of one layer in the ncu --set full capture "
+                                  "profiles/r01_launches_step_b8_v2.md (equals their algorithmic bytes)",
                 "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                 "launches_per_step": len(events), "gemm_ms_per_step": gemm_ms,
                 "share_of_step": gemm_ms / ms_step}
