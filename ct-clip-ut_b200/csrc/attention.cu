@@ -1000,6 +1000,249 @@ attn_small_bwd_kernel(const AttnParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Spatial attention forward on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// One CTA per (frame, head), two CTAs per SM (256 of the 512 TMEM columns each).  K^ (normalised, 64-byte rows,
+// SWIZZLE_64B K-major = the tile_off() layout) and V^T (32 rows x keys, SWIZZLE_128B K-major) stay resident in shared
+// memory; the CTA walks its query rows in M-tiles of 128 (= the 128 TMEM lanes) and the keys in tiles of 128:
+//   MMA thread   : S  = Q^ K^T            tcgen05.mma SS, M128 x N128 x K32 (two K16 steps) -> TMEM cols [0,128)
+//   softmax warps: thread = query row (no shuffles): tcgen05.ld S, + bias pair table, p = exp2(s - shift),
+//                  row sum in a register, P as bf16 pairs -> tcgen05.st into TMEM cols [128,192)
+//   MMA thread   : O += P V               tcgen05.mma TS (A = P from TMEM), M128 x N32, K16 per 16 keys -> cols [192,224)
+// The softmax needs NO running maximum: q^ and k^ are l2-normalised, so every score is bounded by
+// shift = scale * max|q_scale| * max|k_scale| + max|bias| (a property of the weights, supplied by the host), and
+// softmax(s) = exp(s - shift) / sum exp(s - shift) exactly; with shift < 43 nothing can overflow or vanish in fp32.
+// Hence there is no rescaling of O and no cross-lane reduction anywhere.
+// ---------------------------------------------------------------------------------------------
+static constexpr int TC_M = 128, TC_NT = 128, TC_THREADS = 160;
+static constexpr uint32_t TC_TMEM_COLS = 256, TC_COL_S = 0, TC_COL_P = 128, TC_COL_O = 192;
+
+CTC_DEVINL uint64_t make_umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;             // leading byte offset: unused for swizzled K-major
+    d |= static_cast<uint64_t>(512 >> 4) << 32;      // stride byte offset: 8 rows x 64 B
+    d |= static_cast<uint64_t>(1) << 46;             // descriptor version (sm_100)
+    d |= static_cast<uint64_t>(4) << 61;             // SWIZZLE_64B
+    return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+CTC_DEVINL void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+CTC_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+CTC_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
+    extern __shared__ uint8_t sm_raw[];
+    uint8_t* smb = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
+    const int s = blockIdx.x, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = p.n, n_pad = p.n_pad;                               // n_pad: multiple of 64
+    const int nW = 2 * p.W - 1, nb = (2 * p.H - 1) * nW;
+    uint8_t* qs = smb;                                                // [128][64 B]          SWIZZLE_64B
+    uint8_t* ks = qs + TC_M * 64;                                     // [n_pad][64 B]        SWIZZLE_64B
+    uint8_t* vt = ks + n_pad * 64;                                    // [n_pad/64][32][128B] SWIZZLE_128B
+    float2* pair = reinterpret_cast<float2*>(vt + n_pad * 64);        // [nb]
+    int* tab8 = reinterpret_cast<int*>(pair + ((nb + 1) & ~1));       // [n_pad / 8], 16-byte aligned
+    float* sv = reinterpret_cast<float*>(tab8 + ((n_pad / 8 + 3) & ~3));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sv + 64);            // s_full, p_full, pv_done
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* s_full = bars, *p_full = bars + 1, *pv_done = bars + 2;
+
+    if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
+    else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
+    if (threadIdx.x == 0) {
+        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    {   // bias pair table with the softmax shift folded in, and the per-8-key block index table
+        const float* tb = p.bias_table + (long long)head * nb;
+        for (int k = threadIdx.x; k < nb; k += blockDim.x)
+            pair[k] = make_float2(tb[k] * LOG2E - shift2, (k > 0 ? tb[k - 1] * LOG2E : 0.f) - shift2);
+        for (int jb = threadIdx.x; jb < n_pad / 8; jb += blockDim.x) {
+            const int j = min(jb * 8, n - 8);
+            tab8[jb] = (j / p.W) * nW + (j % p.W);
+        }
+    }
+    __syncthreads();
+    load_tile<true>(ks, 0, p.k, p.ldkv, p, s, head, 1, 0, n_pad, sv + 32, 1.0f);
+    // V^T: element (d, key j) at block j/64, row d, 16-byte chunk ((j%64)/8) ^ (d%8), slot j%8
+    for (int j = threadIdx.x; j < n_pad; j += blockDim.x) {
+        uint4 c[4];
+        if (j < n) {
+            const uint4* g = reinterpret_cast<const uint4*>(p.v + seq_row(p, s, j) * p.ldkv + head * DH);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = g[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = make_uint4(0, 0, 0, 0);
+        }
+        uint8_t* blk = vt + (j >> 6) * 4096 + (j & 7) * 2;
+        const int ch = (j & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t w[4] = {c[q].x, c[q].y, c[q].z, c[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int d0 = q * 8 + e * 2;
+                *reinterpret_cast<uint16_t*>(blk + d0 * 128 + ((ch ^ (d0 & 7)) << 4)) = (uint16_t)(w[e] & 0xFFFFu);
+                *reinterpret_cast<uint16_t*>(blk + (d0 + 1) * 128 + ((ch ^ ((d0 + 1) & 7)) << 4)) = (uint16_t)(w[e] >> 16);
+            }
+        }
+    }
+    if (warp == 4) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t t_s = tmem_base + TC_COL_S, t_p = tmem_base + TC_COL_P, t_o = tmem_base + TC_COL_O;
+
+    const int n_mt = (n + TC_M - 1) / TC_M, n_kt = (n_pad + TC_NT - 1) / TC_NT;
+    uint32_t tiles_done = 0;                                          // key tiles completed so far (all threads agree)
+    for (int mt = 0; mt < n_mt; ++mt) {
+        load_tile<true>(qs, 0, p.q, p.ldq, p, s, head, 1, mt * TC_M, TC_M, sv, p.scale * LOG2E);
+        fence_proxy_async();
+        __syncthreads();
+        tcgen05_fence_after();
+        if (warp == 4) {
+            if (lane == 0) {
+                const uint64_t dq = make_umma_desc_sw64(smem_u32(qs));
+                auto issue_s = [&](int kt) {
+                    const int nj = min(TC_NT, n_pad - kt * TC_NT);
+                    const uint32_t idesc = make_idesc_bf16(TC_M, nj);
+                    const uint64_t dk = make_umma_desc_sw64(smem_u32(ks + kt * TC_NT * 64));
+                    umma_f16_ss(t_s, dq, dk, idesc, 0u);
+                    umma_f16_ss(t_s, dq + 2, dk + 2, idesc, 1u);      // second K16 step: +32 B inside the 64 B row
+                    umma_commit(s_full);
+                };
+                issue_s(0);
+                for (int kt = 0; kt < n_kt; ++kt) {
+                    const uint32_t t = tiles_done + kt;
+                    const int nj = min(TC_NT, n_pad - kt * TC_NT);
+                    mbar_wait(p_full, t & 1);                         // P(t) is in TMEM, S(t) has been read
+                    tcgen05_fence_after();
+                    const uint32_t idesc_o = make_idesc_bf16(TC_M, DH);
+                    for (int kk = 0; kk < nj / 16; ++kk) {
+                        const int key0 = kt * TC_NT + kk * 16;
+                        const uint64_t dv = make_umma_desc_sw128(smem_u32(vt + (key0 >> 6) * 4096)) +
+                                            (uint64_t)(((key0 & 63) * 2) >> 4);
+                        umma_f16_ts(t_o, t_p + kk * 8, dv, idesc_o, (kt > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(pv_done);
+                    if (kt + 1 < n_kt) issue_s(kt + 1);
+                }
+            }
+        } else {
+            const int r = warp * 32 + lane;                           // TMEM lane = query row of the tile
+            const int i = mt * TC_M + r;
+            const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+            const int base_i = bias_base(p, i);
+            float l = 0.f;
+            for (int kt = 0; kt < n_kt; ++kt) {
+                const uint32_t t = tiles_done + kt;
+                const int nj = min(TC_NT, n_pad - kt * TC_NT);
+                mbar_wait(s_full, t & 1);
+                tcgen05_fence_after();
+                for (int half = 0; half < nj / 64; ++half) {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(t_s + lane_sel + half * 64 + c2 * 32, v);
+                        const int key0 = kt * TC_NT + half * 64 + c2 * 32;
+                        const int4 tb4 = *reinterpret_cast<const int4*>(tab8 + key0 / 8);
+                        const int tb[4] = {tb4.x, tb4.y, tb4.z, tb4.w};
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 f = pair[base_i - tb[b] - 2 * u];
+                                const int e = b * 8 + 2 * u;
+                                const float p0 = fast_exp2(__uint_as_float(v[e]) + f.x);
+                                const float p1 = fast_exp2(__uint_as_float(v[e + 1]) + f.y);
+                                l += p0 + p1;
+                                pk[c2 * 16 + b * 4 + u] = pack_bf16(p0, p1);
+                            }
+                    }
+                    if (half == 0 && t > 0) {                         // P(t-1) must have been consumed by its PV MMAs
+                        mbar_wait(pv_done, (t - 1) & 1);
+                        tcgen05_fence_after();
+                    }
+                    tmem_st_32x32b_x32(t_p + lane_sel + half * 32, pk);
+                }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+            }
+            mbar_wait(pv_done, (tiles_done + n_kt - 1) & 1);          // O of this M-tile is complete
+            tcgen05_fence_after();
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_o + lane_sel, o);
+            tmem_ld_wait();
+            if (i < n) {
+                const float inv = 1.f / l;
+                const long long row = seq_row(p, s, i);
+                uint4* orow = reinterpret_cast<uint4*>(p.out + row * (p.heads * DH) + head * DH);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    orow[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv),
+                                         pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv),
+                                         pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv),
+                                         pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv));
+                p.lse[row * p.heads + head] = (log2f(l) + shift2) * LN2;
+            }
+            tcgen05_fence_before();
+        }
+        tiles_done += n_kt;
+        __syncthreads();                                              // Q tile, S / P / O columns are free again
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tcgen05_fence_after();
+        tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+    }
+}
+
+// max_h ( scale * max|q_scale| * max|k_scale| + max|bias_h| ): the bound on every attention score (natural units)
+__global__ void attn_score_bound_kernel(const float* __restrict__ q_scale, const float* __restrict__ k_scale, float scale,
+                                        const float* __restrict__ bias_table, int n_bias, float* __restrict__ out) {
+    __shared__ float red[32];
+    float mq = 0.f, mk = 0.f, mb = 0.f;
+    if (threadIdx.x < DH) { mq = fabsf(q_scale[threadIdx.x]); mk = fabsf(k_scale[threadIdx.x]); }
+    for (int i = threadIdx.x; bias_table && i < n_bias; i += blockDim.x) mb = fmaxf(mb, fabsf(bias_table[i]));
+    mq = warp_max(mq); mk = warp_max(mk); mb = warp_max(mb);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[warp] = mb;
+    __syncthreads();
+    if (warp == 0) {
+        float m = (lane < (int)(blockDim.x >> 5)) ? red[lane] : 0.f;
+        m = warp_max(m);
+        if (lane == 0) out[0] = scale * mq * mk + m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: configuration selection and launches
 // ---------------------------------------------------------------------------------------------
 static int fill_params(AttnParams& p, int B, int T, int H, int W, int heads, int mode, int kblk) {
@@ -1099,9 +1342,52 @@ static int run_small_bwd(const AttnParams& p, cudaStream_t st) {
     return launch_attn<attn_small_bwd_kernel>(p, dim3(grid), SMALL_BWD_WARPS * 32, smem, st);
 }
 
+static int run_tc_fwd(const AttnParams& p, float score_bound, cudaStream_t st) {
+    const size_t nb = (size_t)(2 * p.H - 1) * (2 * p.W - 1);
+    const size_t smem = 1024 + (size_t)TC_M * 64 + (size_t)p.n_pad * 128 + ((nb + 1) & ~(size_t)1) * 8 +
+                        (((size_t)p.n_pad / 8 + 3) & ~(size_t)3) * 4 + 256 + 64;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            (int)cudaSharedmemCarveoutMaxShared));
+        configured = smem;
+    }
+    attn_tc_fwd_kernel<<<dim3(p.n_seq, p.heads), TC_THREADS, smem, st>>>(p, score_bound * LOG2E);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace ctc
 
 using namespace ctc;
+
+extern "C" int ctc_attention_score_bound(const float* q_scale, const float* k_scale, float scale,
+                                         const float* bias_table, int heads, int H, int W, float* bound_dev,
+                                         void* stream) {
+    attn_score_bound_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(q_scale, k_scale, scale, bias_table,
+                                                                 heads * (2 * H - 1) * (2 * W - 1), bound_dev);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_attention_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int B, int T,
+                                    int H, int W, int heads, const float* q_scale, const float* k_scale, float scale,
+                                    const float* bias_table, float score_bound, void* o, float* lse, void* stream) {
+    AttnParams p{};
+    p.bias_table = bias_table;
+    if (int e = fill_params(p, B, T, H, W, heads, CTC_MODE_SPATIAL, 64)) return e;
+    CTC_REQUIRE(bias_table != nullptr && p.n % 64 == 0 && W % 8 == 0 && p.n_pad * 128 + 30000 <= 110 * 1024,
+                "attention_fwd_tc: needs the spatial geometry (bias table, H*W %% 64 == 0, W %% 8 == 0, H*W <= 640); got "
+                "H=%d W=%d", H, W);
+    CTC_REQUIRE(score_bound > 0.f && score_bound < 43.f,
+                "attention_fwd_tc: score bound %.2f outside (0, 43): the fixed-shift softmax is not safe, use ctc_attention_fwd",
+                score_bound);
+    p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v;
+    p.ldkv = ldkv; p.q_scale = q_scale; p.k_scale = k_scale; p.scale = scale;
+    p.out = (__nv_bfloat16*)o; p.lse = lse;
+    return run_tc_fwd(p, score_bound, (cudaStream_t)stream);
+}
 
 extern "C" int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int B, int T,
                                  int H, int W, int heads, const float* q_scale, const float* k_scale, float scale,

@@ -31,6 +31,8 @@ SIGNATURES = {
     "ctc_frames_gather": [P, P, P, I, L, P, P],
     "ctc_rows_fill": [P, P, I, I, P, P],
     "ctc_attention_fwd": [P, L, P, P, L, I, I, I, I, I, P, P, F, P, I, P, P, P],
+    "ctc_attention_fwd_tc": [P, L, P, P, L, I, I, I, I, I, P, P, F, P, F, P, P, P],
+    "ctc_attention_score_bound": [P, P, F, P, I, I, I, P, P],
     "ctc_attention_bwd": [P, L, P, P, L, P, P, P, I, I, I, I, I, P, P, F, P, I, P, L, P, P, L, P, P],
     "ctc_attention_probs": [P, L, P, L, P, I, I, I, I, I, P, P, F, P, I, P, P],
     "ctc_geglu_fwd": [P, I, I, P, P],

@@ -131,6 +131,7 @@ class Engine:
         self.dev = plan.device
         self.gemm_impl = gemm_impl
         self.fuse_geglu_bwd = False
+        self.attn_tc = True          # spatial attention forward on tcgen05/TMEM (ctc_attention_fwd_tc)
         self._row_cap = 0
 
     # ------------------------------------------------------------------ helpers
@@ -195,9 +196,15 @@ class Engine:
         q = self.gemm(xn, lw.wq, self._empty(R, inner, dtype=bf), EPI_BF16)
         kv = self.gemm(xraw, lw.wkv, self._empty(R, 2 * inner, dtype=bf), EPI_BF16)
         o, lse = self._empty(R, inner, dtype=bf), self._empty(R, cfg.heads)
-        call("ctc_attention_fwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, cfg.heads,
-             lw.q_scale, lw.k_scale, cfg.attn_scale, self.plan.bias_table if mode == MODE_SPATIAL else None, mode,
-             o, lse, stream_ptr())
+        if (mode == MODE_SPATIAL and self.attn_tc and (H * W) % 64 == 0 and W % 8 == 0 and H * W <= 640
+                and 0.0 < getattr(lw, "score_bound", 0.0) < 43.0):
+            # tcgen05 / TMEM kernel with the fixed-shift softmax (scores are bounded by lw.score_bound)
+            call("ctc_attention_fwd_tc", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, cfg.heads,
+                 lw.q_scale, lw.k_scale, cfg.attn_scale, self.plan.bias_table, lw.score_bound, o, lse, stream_ptr())
+        else:
+            call("ctc_attention_fwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, cfg.heads,
+                 lw.q_scale, lw.k_scale, cfg.attn_scale, self.plan.bias_table if mode == MODE_SPATIAL else None, mode,
+                 o, lse, stream_ptr())
         # x = to_out(attn) + x                                             attention.py:182, 328
         x2 = self.gemm(o, lw.wout, self._empty(R, C), EPI_F32, resid=x1)
         # x = ff(x) + x                                                    attention.py:43-51, 334

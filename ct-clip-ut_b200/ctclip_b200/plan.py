@@ -97,6 +97,13 @@ class Plan:
 
         self.spatial = [self._layer(sd, f"{vt}enc_spatial_transformer.layers.{i}.") for i in range(cfg.spatial_depth)]
         self.temporal = [self._layer(sd, f"{vt}enc_temporal_transformer.layers.{i}.") for i in range(cfg.temporal_depth)]
+        # bound on every spatial attention score, scale*max|q_scale|*max|k_scale| + max|bias| (attention.py:160-172:
+        # q, k are l2-normalised): lets the tcgen05 attention kernel use a fixed softmax shift instead of a running max
+        bound = torch.empty(1, device=dev, dtype=torch.float32)
+        for lw in self.spatial:
+            _lib.call("ctc_attention_score_bound", lw.q_scale, lw.k_scale, cfg.attn_scale, self.bias_table, cfg.heads, hw,
+                      hw, bound, _lib.stream_ptr())
+            lw.score_bound = float(bound.item())
         self.spatial_norm_g = f32(vt + "enc_spatial_transformer.norm_out.gamma")
         self.spatial_norm_b = f32(vt + "enc_spatial_transformer.norm_out.beta")
         self.temporal_norm_g = f32(vt + "enc_temporal_transformer.norm_out.gamma")

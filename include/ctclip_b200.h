@@ -107,6 +107,15 @@ int ctc_rows_fill(float* x, const int* rows, int n_rows, int C, const float* val
 int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int B, int T, int H,
                       int W, int heads, const float* q_scale, const float* k_scale, float scale,
                       const float* bias_table, int mode, void* o, float* lse, void* stream);
+/* The same forward for the SPATIAL sequences on tcgen05 / TMEM (S = Q K^T and O = P V as tcgen05.mma with P fed
+ * from tensor memory).  score_bound must bound every attention score: scale*max|q_scale|*max|k_scale| + max|bias|
+ * (ctc_attention_score_bound writes it to a device float); it replaces the running row maximum of the softmax.
+ * Needs H*W % 64 == 0, W % 8 == 0, H*W <= 640, 0 < score_bound < 43; otherwise use ctc_attention_fwd. */
+int ctc_attention_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int B, int T, int H,
+                         int W, int heads, const float* q_scale, const float* k_scale, float scale,
+                         const float* bias_table, float score_bound, void* o, float* lse, void* stream);
+int ctc_attention_score_bound(const float* q_scale, const float* k_scale, float scale, const float* bias_table,
+                              int heads, int H, int W, float* bound_dev, void* stream);
 /* Input gradients of the above (through softmax, l2norm and q/k scales). dq bf16 [R,heads*32] (lddq),
  * dk/dv bf16 (lddkv). delta_ws fp32 [R, heads] scratch. */
 int ctc_attention_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* o,

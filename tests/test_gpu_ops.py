@@ -264,6 +264,41 @@ def test_attention_fwd_bwd_probs(lib, mode, B, T, H, W, heads):
     assert relerr(dkv[:, inner:], dkv_ref[:, inner:]) < 4e-2
 
 
+@pytest.mark.parametrize("B,T,H,W,heads", [(1, 2, 24, 24, 8), (1, 3, 8, 8, 2), (2, 1, 16, 8, 1), (1, 1, 16, 16, 2)])
+def test_attention_fwd_tcgen05_matches_reference_and_mma_sync(lib, B, T, H, W, heads):
+    """Spatial attention forward on tcgen05/TMEM with the fixed-shift softmax (attention.py:144-180) against the fp32
+    torch restatement and against the mma.sync kernel (same bf16 operands: outputs agree to bf16 rounding)."""
+    R, inner = B * T * H * W, heads * 32
+    q = rnd(R, inner, seed=1, dtype=torch.bfloat16)
+    kv = rnd(R, 2 * inner, seed=2, dtype=torch.bfloat16)
+    qs = 1 + 0.1 * rnd(32, seed=3)
+    ks = 1 + 0.1 * rnd(32, seed=4)
+    table = rnd(heads, (2 * H - 1) * (2 * W - 1), seed=5, scale=0.5)
+    ii = torch.arange(H * W, device=dev())
+    hi, wi = ii // W, ii % W
+    idx = (hi[:, None] - hi[None, :] + H - 1) * (2 * W - 1) + (wi[:, None] - wi[None, :] + W - 1)
+    bias = table[:, idx]
+    bound_t = torch.empty(1, device=dev())
+    lib.call("ctc_attention_score_bound", qs, ks, 8.0, table, heads, H, W, bound_t, lib.stream_ptr())
+    bound = float(bound_t)
+    assert abs(bound - float(8.0 * qs.abs().max() * ks.abs().max() + table.abs().max())) < 1e-4
+    o = torch.full((R, inner), float("nan"), device=dev(), dtype=torch.bfloat16)
+    lse = torch.full((R, heads), float("nan"), device=dev())
+    lib.call("ctc_attention_fwd_tc", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, heads, qs, ks, 8.0,
+             table, bound, o, lse, lib.stream_ptr())
+    torch.cuda.synchronize()
+    o_ref, lse_ref, _ = _attn_ref(q.float(), kv.float(), qs, ks, 8.0, bias, B, T, H, W, heads, 0)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert relerr(o, o_ref) < 2e-2
+    assert float((lse - lse_ref).abs().max()) < 2e-2
+    o2 = torch.empty_like(o)
+    lse2 = torch.empty_like(lse)
+    lib.call("ctc_attention_fwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, heads, qs, ks, 8.0,
+             table, 0, o2, lse2, lib.stream_ptr())
+    assert relerr(o, o2.float()) < 1e-2
+    assert float((lse - lse2).abs().max()) < 1e-3
+
+
 # --------------------------------------------------------------------------------------- GEGLU
 def _group(x_part, gate_part):
     """[R,F],[R,F] -> grouped [R, 2F]: 64-wide groups [32 value | 32 gate]"""

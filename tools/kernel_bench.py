@@ -68,3 +68,11 @@ for mode, tag in ((1, "attn_t"), (0, "attn_s")):
         L.call("ctc_attention_bwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, o, d_o, lse, B, T, H, W, heads,
                qs, ks, 8.0, table, mode, dq, inner, dkv, dkv.data_ptr() + inner * 2, 2 * inner, delta, L.stream_ptr())
     print(f"  {tag} fwd {timeit(fwd):8.1f} us   bwd (dq + dkv) {timeit(bwd):8.1f} us")
+    if mode == 0:
+        bt = torch.empty(1, device=dev)
+        L.call("ctc_attention_score_bound", qs, ks, 8.0, table, heads, H, W, bt, L.stream_ptr())
+        bound = float(bt)
+        def fwd_tc():
+            L.call("ctc_attention_fwd_tc", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, heads, qs, ks,
+                   8.0, table, bound, o, lse, L.stream_ptr())
+        print(f"  {tag} fwd tcgen05 {timeit(fwd_tc):8.1f} us (score bound {bound:.2f})")
