@@ -1014,8 +1014,12 @@ attn_small_bwd_kernel(const AttnParams p) {
 // softmax(s) = exp(s - shift) / sum exp(s - shift) exactly; with shift < 43 nothing can overflow or vanish in fp32.
 // Hence there is no rescaling of O and no cross-lane reduction anywhere.
 // ---------------------------------------------------------------------------------------------
-static constexpr int TC_M = 128, TC_NT = 128, TC_THREADS = 160;
-static constexpr uint32_t TC_TMEM_COLS = 256, TC_COL_S = 0, TC_COL_P = 128, TC_COL_O = 192;
+static constexpr int TC_M = 128, TC_NT = 64;
+static constexpr int TC_SOFTMAX_WARPS = 8;                 // two per TMEM lane quarter: each owns 32 of a tile's 64 keys
+static constexpr int TC_WARP_MMA = 8, TC_WARP_LOAD = 9;
+static constexpr int TC_THREADS = 320;
+static constexpr uint32_t TC_TMEM_COLS = 256;              // S 2 x 64 | P 2 x 32 | O 2 x 32
+static constexpr uint32_t TC_COL_S = 0, TC_COL_P = 128, TC_COL_O = 192;
 
 CTC_DEVINL uint64_t make_umma_desc_sw64(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -1035,19 +1039,82 @@ CTC_DEVINL void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, u
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-CTC_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+CTC_DEVINL void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+CTC_DEVINL void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+CTC_DEVINL void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 CTC_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// bf16x2 pack of two POSITIVE finite floats on the integer pipe (round half up: add 0x8000, keep the high halves),
+// keeping the conversion off the XU pipe that the exponentials saturate
+CTC_DEVINL uint32_t pack_bf16_rn_alu(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+CTC_DEVINL void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+// normalise rows [row0, row0 + 128) of q into a SWIZZLE_64B tile; `nthreads` threads starting at `tid0` cooperate
+CTC_DEVINL void tc_load_q(uint8_t* tile, const AttnParams& p, int s, int head, int row0, const float* sv, int tid,
+                          int nthreads) {
+    for (int r = tid; r < TC_M; r += nthreads) {
+        const int i = row0 + r;
+        uint4 c[4];
+        if (i < p.n) {
+            const uint4* g = reinterpret_cast<const uint4*>(p.q + seq_row(p, s, i) * p.ldq + head * DH);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = g[j];
+            float f[32];
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 t = unpack_bf16(w[e]);
+                    f[j * 8 + e * 2] = t.x; f[j * 8 + e * 2 + 1] = t.y;
+                    ss += t.x * t.x + t.y * t.y;
+                }
+            }
+            const float inv = p.scale * LOG2E / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                c[j].x = pack_bf16(f[j * 8 + 0] * inv * sv[j * 8 + 0], f[j * 8 + 1] * inv * sv[j * 8 + 1]);
+                c[j].y = pack_bf16(f[j * 8 + 2] * inv * sv[j * 8 + 2], f[j * 8 + 3] * inv * sv[j * 8 + 3]);
+                c[j].z = pack_bf16(f[j * 8 + 4] * inv * sv[j * 8 + 4], f[j * 8 + 5] * inv * sv[j * 8 + 5]);
+                c[j].w = pack_bf16(f[j * 8 + 6] * inv * sv[j * 8 + 6], f[j * 8 + 7] * inv * sv[j * 8 + 7]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(tile + tile_off(r, j)) = c[j];
+    }
+}
+
+// Pipeline (t = global key-tile counter of the CTA, b = t & 1 selects the S / P buffer):
+//   MMA thread : S(t) -> s_full[b];  after p_full[b]: PV(t) -> pv_done[b], then S(t+2) into the S buffer just read
+//   softmax    : wait s_full[b]; tcgen05.ld; exp2; wait pv_done[b] of tile t-2; tcgen05.st P(t) -> p_full[b]
+// so the tensor core computes S(t+1) while the softmax warps work on S(t), and no warp waits on a barrier round trip.
+// The stream of key tiles runs straight through the M-tile boundaries: O is double-buffered (o_free), the next Q tile
+// is normalised by a loader warp into the other Q buffer (q_full / q_free), and there is no CTA barrier in the loop.
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
     extern __shared__ uint8_t sm_raw[];
@@ -1056,20 +1123,25 @@ attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = p.n, n_pad = p.n_pad;                               // n_pad: multiple of 64
     const int nW = 2 * p.W - 1, nb = (2 * p.H - 1) * nW;
-    uint8_t* qs = smb;                                                // [128][64 B]          SWIZZLE_64B
-    uint8_t* ks = qs + TC_M * 64;                                     // [n_pad][64 B]        SWIZZLE_64B
+    uint8_t* qs = smb;                                                // [2][128][64 B]       SWIZZLE_64B
+    uint8_t* ks = qs + 2 * TC_M * 64;                                 // [n_pad][64 B]        SWIZZLE_64B
     uint8_t* vt = ks + n_pad * 64;                                    // [n_pad/64][32][128B] SWIZZLE_128B
     float2* pair = reinterpret_cast<float2*>(vt + n_pad * 64);        // [nb]
     int* tab8 = reinterpret_cast<int*>(pair + ((nb + 1) & ~1));       // [n_pad / 8], 16-byte aligned
     float* sv = reinterpret_cast<float*>(tab8 + ((n_pad / 8 + 3) & ~3));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sv + 64);            // s_full, p_full, pv_done
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
-    uint64_t* s_full = bars, *p_full = bars + 1, *pv_done = bars + 2;
+    float* lsum = sv + 64;                                            // [128] row-sum exchange between the column halves
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lsum + TC_M);        // 6 x [2] barriers
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* s_full = bars, *p_full = bars + 2, *pv_done = bars + 4, *q_full = bars + 6, *q_free = bars + 8,
+              *o_free = bars + 10;
 
     if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
     else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
     if (threadIdx.x == 0) {
-        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&s_full[b], 1); mbar_init(&p_full[b], TC_SOFTMAX_WARPS); mbar_init(&pv_done[b], 1);
+            mbar_init(&q_full[b], 1); mbar_init(&q_free[b], 1); mbar_init(&o_free[b], TC_SOFTMAX_WARPS);
+        }
         fence_barrier_init();
     }
     {   // bias pair table with the softmax shift folded in, and the per-8-key block index table
@@ -1107,118 +1179,138 @@ attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
             }
         }
     }
-    if (warp == 4) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
+    tc_load_q(qs, p, s, head, 0, sv, threadIdx.x, blockDim.x);        // first Q tile by everybody
+    if (warp == TC_WARP_MMA) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t t_s = tmem_base + TC_COL_S, t_p = tmem_base + TC_COL_P, t_o = tmem_base + TC_COL_O;
 
-    const int n_mt = (n + TC_M - 1) / TC_M, n_kt = (n_pad + TC_NT - 1) / TC_NT;
-    uint32_t tiles_done = 0;                                          // key tiles completed so far (all threads agree)
-    for (int mt = 0; mt < n_mt; ++mt) {
-        load_tile<true>(qs, 0, p.q, p.ldq, p, s, head, 1, mt * TC_M, TC_M, sv, p.scale * LOG2E);
-        fence_proxy_async();
-        __syncthreads();
-        tcgen05_fence_after();
-        if (warp == 4) {
-            if (lane == 0) {
-                const uint64_t dq = make_umma_desc_sw64(smem_u32(qs));
-                auto issue_s = [&](int kt) {
-                    const int nj = min(TC_NT, n_pad - kt * TC_NT);
-                    const uint32_t idesc = make_idesc_bf16(TC_M, nj);
-                    const uint64_t dk = make_umma_desc_sw64(smem_u32(ks + kt * TC_NT * 64));
-                    umma_f16_ss(t_s, dq, dk, idesc, 0u);
-                    umma_f16_ss(t_s, dq + 2, dk + 2, idesc, 1u);      // second K16 step: +32 B inside the 64 B row
-                    umma_commit(s_full);
-                };
-                issue_s(0);
-                for (int kt = 0; kt < n_kt; ++kt) {
-                    const uint32_t t = tiles_done + kt;
-                    const int nj = min(TC_NT, n_pad - kt * TC_NT);
-                    mbar_wait(p_full, t & 1);                         // P(t) is in TMEM, S(t) has been read
+    const int n_mt = (n + TC_M - 1) / TC_M, n_kt = n_pad / TC_NT;
+    const int n_tiles = n_mt * n_kt;
+    if (warp == TC_WARP_MMA) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_bf16(TC_M, TC_NT), idesc_o = make_idesc_bf16(TC_M, DH);
+            auto issue_s = [&](int t) {                               // S(t) = Q(mt) K(kt)^T into S buffer t & 1
+                const int mt = t / n_kt, kt = t - mt * n_kt;
+                if (kt == 0 && mt > 0) {                              // first use of this M-tile's Q buffer
+                    mbar_wait(&q_full[mt & 1], (((mt + 1) >> 1) - 1) & 1);
                     tcgen05_fence_after();
-                    const uint32_t idesc_o = make_idesc_bf16(TC_M, DH);
-                    for (int kk = 0; kk < nj / 16; ++kk) {
-                        const int key0 = kt * TC_NT + kk * 16;
-                        const uint64_t dv = make_umma_desc_sw128(smem_u32(vt + (key0 >> 6) * 4096)) +
-                                            (uint64_t)(((key0 & 63) * 2) >> 4);
-                        umma_f16_ts(t_o, t_p + kk * 8, dv, idesc_o, (kt > 0 || kk > 0) ? 1u : 0u);
-                    }
-                    umma_commit(pv_done);
-                    if (kt + 1 < n_kt) issue_s(kt + 1);
                 }
+                const uint64_t dq = make_umma_desc_sw64(smem_u32(qs + (mt & 1) * TC_M * 64));
+                const uint64_t dk = make_umma_desc_sw64(smem_u32(ks + kt * TC_NT * 64));
+                const uint32_t ts = tmem_base + TC_COL_S + (t & 1) * TC_NT;
+                umma_f16_ss(ts, dq, dk, idesc_s, 0u);
+                umma_f16_ss(ts, dq + 2, dk + 2, idesc_s, 1u);         // second K16 step: +32 B inside the 64 B row
+                umma_commit(&s_full[t & 1]);
+                if (kt == n_kt - 1) umma_commit(&q_free[mt & 1]);     // every S of this M-tile has been issued
+            };
+            issue_s(0);
+            if (n_tiles > 1) issue_s(1);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int mt = t / n_kt, kt = t - mt * n_kt;
+                const uint32_t b = t & 1;
+                mbar_wait(&p_full[b], (t >> 1) & 1);                  // P(t) is in TMEM, S(t) has been read
+                if (kt == 0 && mt >= 2) mbar_wait(&o_free[mt & 1], ((mt >> 1) - 1) & 1);   // O of M-tile mt-2 was read
+                tcgen05_fence_after();
+                const uint64_t dv = make_umma_desc_sw128(smem_u32(vt + kt * 4096));
+                const uint32_t tp = tmem_base + TC_COL_P + b * (TC_NT / 2);
+                const uint32_t to = tmem_base + TC_COL_O + (mt & 1) * DH;
+#pragma unroll
+                for (int kk = 0; kk < TC_NT / 16; ++kk)
+                    umma_f16_ts(to, tp + kk * 8, dv + (uint64_t)(kk * 2), idesc_o, (kt > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(&pv_done[b]);
+                if (t + 2 < n_tiles) issue_s(t + 2);
             }
-        } else {
-            const int r = warp * 32 + lane;                           // TMEM lane = query row of the tile
+        }
+    } else if (warp == TC_WARP_LOAD) {
+        // Q rows of M-tile m into buffer m & 1 as soon as the S MMAs of M-tile m - 2 no longer read it
+        for (int m = 1; m < n_mt; ++m) {
+            if (m >= 2) mbar_wait(&q_free[m & 1], ((m >> 1) - 1) & 1);
+            tc_load_q(qs + (m & 1) * TC_M * 64, p, s, head, m * TC_M, sv, lane, 32);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_full[m & 1]);
+        }
+    } else {
+        const int quarter = warp & 3, chalf = warp >> 2;              // TMEM lane quarter, column half of the key tile
+        const int r = quarter * 32 + lane;                            // TMEM lane = query row of the tile
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        for (int mt = 0; mt < n_mt; ++mt) {
             const int i = mt * TC_M + r;
-            const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
             const int base_i = bias_base(p, i);
             float l = 0.f;
             for (int kt = 0; kt < n_kt; ++kt) {
-                const uint32_t t = tiles_done + kt;
-                const int nj = min(TC_NT, n_pad - kt * TC_NT);
-                mbar_wait(s_full, t & 1);
+                const uint32_t t = mt * n_kt + kt, b = t & 1;
+                mbar_wait(&s_full[b], (t >> 1) & 1);
                 tcgen05_fence_after();
-                for (int half = 0; half < nj / 64; ++half) {
-                    uint32_t pk[32];
+                // four 8-column loads, each in flight while the previous 8 scores are exponentiated: TMEM reads
+                // (64 B/clk/SM) and the MUFU pipe (16 exp/clk/SM) have the same floor here and must overlap
+                const uint32_t ts = tmem_base + TC_COL_S + b * TC_NT + lane_sel + chalf * 32;
+                const int key0 = kt * TC_NT + chalf * 32;
+                const int4 tb4 = *reinterpret_cast<const int4*>(tab8 + key0 / 8);
+                const int tb[4] = {tb4.x, tb4.y, tb4.z, tb4.w};
+                uint32_t pk[16];
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                uint32_t v[2][8];
+                tmem_ld_32x32b_x8(ts, v[0]);
 #pragma unroll
-                    for (int c2 = 0; c2 < 2; ++c2) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(t_s + lane_sel + half * 64 + c2 * 32, v);
-                        const int key0 = kt * TC_NT + half * 64 + c2 * 32;
-                        const int4 tb4 = *reinterpret_cast<const int4*>(tab8 + key0 / 8);
-                        const int tb[4] = {tb4.x, tb4.y, tb4.z, tb4.w};
-                        tmem_ld_wait();
+                for (int bb = 0; bb < 4; ++bb) {
+                    tmem_ld_wait();
+                    if (bb < 3) tmem_ld_32x32b_x8(ts + (bb + 1) * 8, v[(bb + 1) & 1]);
 #pragma unroll
-                        for (int b = 0; b < 4; ++b)
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float2 f = pair[base_i - tb[b] - 2 * u];
-                                const int e = b * 8 + 2 * u;
-                                const float p0 = fast_exp2(__uint_as_float(v[e]) + f.x);
-                                const float p1 = fast_exp2(__uint_as_float(v[e + 1]) + f.y);
-                                l += p0 + p1;
-                                pk[c2 * 16 + b * 4 + u] = pack_bf16(p0, p1);
-                            }
+                    for (int u = 0; u < 4; ++u) {
+                        const float2 f = pair[base_i - tb[bb] - 2 * u];
+                        const float p0 = fast_exp2(__uint_as_float(v[bb & 1][2 * u]) + f.x);
+                        const float p1 = fast_exp2(__uint_as_float(v[bb & 1][2 * u + 1]) + f.y);
+                        if (u & 1) { l1 += p0; l3 += p1; } else { l0 += p0; l2 += p1; }
+                        pk[bb * 4 + u] = pack_bf16(p0, p1);
                     }
-                    if (half == 0 && t > 0) {                         // P(t-1) must have been consumed by its PV MMAs
-                        mbar_wait(pv_done, (t - 1) & 1);
-                        tcgen05_fence_after();
-                    }
-                    tmem_st_32x32b_x32(t_p + lane_sel + half * 32, pk);
                 }
+                l += (l0 + l1) + (l2 + l3);
+                if (t >= 2) {                                         // P(t-2) (same buffer) consumed by its PV MMAs
+                    mbar_wait(&pv_done[b], ((t >> 1) - 1) & 1);
+                    tcgen05_fence_after();
+                }
+                tmem_st_32x32b_x16(tmem_base + TC_COL_P + b * (TC_NT / 2) + lane_sel + chalf * 16, pk);
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(p_full);
+                if (lane == 0) mbar_arrive(&p_full[b]);
             }
-            mbar_wait(pv_done, (tiles_done + n_kt - 1) & 1);          // O of this M-tile is complete
+            // combine the two column halves' row sums, then each half normalises and writes 16 of the 32 output dims
+            if (chalf == 1) lsum[r] = l;
+            named_bar_sync(1, TC_SOFTMAX_WARPS * 32);
+            if (chalf == 0) lsum[r] = l = l + lsum[r];
+            named_bar_sync(1, TC_SOFTMAX_WARPS * 32);
+            l = lsum[r];
+            const uint32_t tl = mt * n_kt + n_kt - 1;
+            mbar_wait(&pv_done[tl & 1], (tl >> 1) & 1);               // the last PV commit covers every earlier MMA
             tcgen05_fence_after();
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(t_o + lane_sel, o);
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tmem_base + TC_COL_O + (mt & 1) * DH + lane_sel + chalf * 16, o);
             tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[mt & 1]);
             if (i < n) {
                 const float inv = 1.f / l;
                 const long long row = seq_row(p, s, i);
-                uint4* orow = reinterpret_cast<uint4*>(p.out + row * (p.heads * DH) + head * DH);
+                uint4* orow = reinterpret_cast<uint4*>(p.out + row * (p.heads * DH) + head * DH + chalf * 16);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 2; ++q)
                     orow[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv),
                                          pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv),
                                          pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv),
                                          pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv));
-                p.lse[row * p.heads + head] = (log2f(l) + shift2) * LN2;
+                if (chalf == 0) p.lse[row * p.heads + head] = (log2f(l) + shift2) * LN2;
             }
-            tcgen05_fence_before();
         }
-        tiles_done += n_kt;
-        __syncthreads();                                              // Q tile, S / P / O columns are free again
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_WARP_MMA) {
         tcgen05_fence_after();
         tmem_dealloc<TC_TMEM_COLS>(tmem_base);
     }
@@ -1344,8 +1436,8 @@ static int run_small_bwd(const AttnParams& p, cudaStream_t st) {
 
 static int run_tc_fwd(const AttnParams& p, float score_bound, cudaStream_t st) {
     const size_t nb = (size_t)(2 * p.H - 1) * (2 * p.W - 1);
-    const size_t smem = 1024 + (size_t)TC_M * 64 + (size_t)p.n_pad * 128 + ((nb + 1) & ~(size_t)1) * 8 +
-                        (((size_t)p.n_pad / 8 + 3) & ~(size_t)3) * 4 + 256 + 64;
+    const size_t smem = 1024 + 2 * (size_t)TC_M * 64 + (size_t)p.n_pad * 128 + ((nb + 1) & ~(size_t)1) * 8 +
+                        (((size_t)p.n_pad / 8 + 3) & ~(size_t)3) * 4 + 256 + TC_M * 4 + 64;
     static size_t configured = 0;
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

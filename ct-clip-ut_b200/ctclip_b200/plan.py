@@ -57,7 +57,7 @@ class Config:
 
 class LayerWeights:
     __slots__ = ("w27", "peg_bias", "ln_g", "ln_b", "q_scale", "k_scale", "wq", "wkv", "wout", "wq_t", "wkv_t",
-                 "wout_t", "ff_ln_w", "ff_ln_b", "w1", "w2", "w1_t", "w2_t")
+                 "wout_t", "ff_ln_w", "ff_ln_b", "w1", "w2", "w1_t", "w2_t", "score_bound")
 
 
 def _bf16(t: torch.Tensor) -> torch.Tensor:

@@ -1,4 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 120 python -m pytest tests/test_gpu_ops.py -q -m gpu -x -k "tcgen05" 2>&1 | grep -v Warning | tail -n 25 > gpurun_out/r30_ops.log
-timeout 120 python tools/kernel_bench.py attn_s > gpurun_out/r30_attn_s.log 2>&1
+timeout 400 python -m pytest tests -q -m gpu -x 2>&1 | grep -v Warning | tail -n 12 > gpurun_out/r32_tests.log
+timeout 200 python tools/time_engine.py 8 > gpurun_out/r32_time_b8.log 2>&1
+timeout 200 python tools/time_occlusion.py 32 > gpurun_out/r32_occ.log 2>&1
 echo done
