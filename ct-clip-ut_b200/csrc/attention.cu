@@ -28,8 +28,8 @@ static constexpr int DH = 32;          // head dim (fixed on this path: inferenc
 // Tile configurations <QB rows per (CTA, head), KBLK keys per softmax step, HPC heads per CTA>:
 //   spatial  (n = 576): one head per CTA, large row tiles so that 12 (fwd) / 6 (bwd) warps share one
 //                       resident K/V copy (occupancy is bounded by the 72 KB K/V tile, not by threads);
-//   temporal (n = 24) : all 8 heads of one (b,h,w) column in one CTA, 32-row tiles, so that the strided
-//                       token rows (q 512 B, kv 1 KB) are each fetched once, fully coalesced.
+//   temporal (n = 24) : forward / backward run on the warp-autonomous kernels further down; the CTA-per-sequence
+//                       configuration <32, 32, 2> only materialises probabilities (attention_probs).
 static constexpr float LOG2E = 1.4426950408889634f;
 static constexpr float LN2 = 0.6931471805599453f;
 
@@ -1362,17 +1362,9 @@ static int launch_attn(const AttnParams& p, dim3 grid, int threads, size_t smem,
     return 0;
 }
 
-// small-sequence configuration (temporal, n <= 32): HPC heads of a sequence per CTA
-static int small_hpc(int heads) {
-    static int pref = -1;
-    if (pref < 0) {
-        const char* e = getenv("CTC_ATTN_SMALL_HPC");
-        pref = e ? atoi(e) : 2;
-    }
-    int h = pref;
-    while (h > 1 && heads % h != 0) h >>= 1;
-    return h < 1 ? 1 : h;
-}
+// small-sequence configuration (temporal, n <= 32) of the CTA-per-sequence kernels: only attention_probs uses them
+// (forward / backward run on the warp-autonomous kernels above); two heads per CTA when the head count is even
+static int small_hpc(int heads) { return heads % 2 == 0 ? 2 : 1; }
 static bool use_small(const AttnParams& p) { return p.n <= 32 && p.bias_table == nullptr; }
 
 // Row blocks of one (sequence, head) are walked by ONE CTA (gridDim.z = 1, resident K/V or Q/dO loaded and
@@ -1414,11 +1406,7 @@ static int run_bwd(AttnParams& p, cudaStream_t st) {
     return launch_attn<attn_bwd_dkv_kernel<QB, KBLK, HPC, false>>(p, grid, threads, smem_dkv, st);
 }
 
-static bool small_warp_path(const AttnParams& p) {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("CTC_ATTN_SMALL_WARP"); on = e ? atoi(e) : 1; }
-    return on && p.n <= SMALL_N && p.bias_table == nullptr;
-}
+static bool small_warp_path(const AttnParams& p) { return p.n <= SMALL_N && p.bias_table == nullptr; }
 static int run_small_fwd(const AttnParams& p, cudaStream_t st) {
     const size_t smem = 256 + (size_t)SMALL_FWD_WARPS * 2 * 3 * SMALL_TILE;
     const int n_tasks = p.n_seq * p.heads;
@@ -1496,7 +1484,7 @@ extern "C" int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, cons
     if (small && small_warp_path(p)) return run_small_fwd(p, st);
     if (small) {
         const int h = small_hpc(heads);
-        return h >= 8 ? run_fwd<32, 32, 8, false>(p, st) : h >= 2 ? run_fwd<32, 32, 2, false>(p, st) : run_fwd<32, 32, 1, false>(p, st);
+        return h >= 2 ? run_fwd<32, 32, 2, false>(p, st) : run_fwd<32, 32, 1, false>(p, st);
     }
     return (p.n > 128) ? run_fwd<192, 64, 1, false>(p, st) : run_fwd<64, 64, 1, false>(p, st);
 }
@@ -1515,7 +1503,7 @@ extern "C" int ctc_attention_probs(const void* q, int64_t ldq, const void* k, in
     cudaStream_t st = (cudaStream_t)stream;
     if (small) {
         const int h = small_hpc(heads);
-        return h >= 8 ? run_fwd<32, 32, 8, true>(p, st) : h >= 2 ? run_fwd<32, 32, 2, true>(p, st) : run_fwd<32, 32, 1, true>(p, st);
+        return h >= 2 ? run_fwd<32, 32, 2, true>(p, st) : run_fwd<32, 32, 1, true>(p, st);
     }
     return (p.n > 128) ? run_fwd<192, 64, 1, true>(p, st) : run_fwd<64, 64, 1, true>(p, st);
 }
@@ -1539,7 +1527,7 @@ extern "C" int ctc_attention_bwd(const void* q, int64_t ldq, const void* k, cons
     if (small && small_warp_path(p)) return run_small_bwd(p, st);
     if (small) {
         const int h = small_hpc(heads);
-        return h >= 8 ? run_bwd<32, 32, 8>(p, st) : h >= 2 ? run_bwd<32, 32, 2>(p, st) : run_bwd<32, 32, 1>(p, st);
+        return h >= 2 ? run_bwd<32, 32, 2>(p, st) : run_bwd<32, 32, 1>(p, st);
     }
     return (p.n > 128) ? run_bwd<96, 64, 1>(p, st) : run_bwd<64, 64, 1>(p, st);
 }

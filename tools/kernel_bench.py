@@ -30,7 +30,6 @@ def rnd(*shape, dtype=torch.float32, scale=1.0):
 
 
 if what in ("gemm", "all"):
-    print(f"env CTC_GEMM_BN256={os.environ.get('CTC_GEMM_BN256', '0')}")
     for name, N, K, epi, resid in [("q", 256, 512, L.EPI_BF16, False), ("kv", 512, 512, L.EPI_BF16, False),
                                    ("out+res", 512, 256, L.EPI_F32, True), ("ff1 geglu (no u)", 2816, 512, L.EPI_GEGLU, False),
                                    ("ff2+res", 512, 1408, L.EPI_F32, True), ("dh", 1408, 512, L.EPI_BF16, False),
@@ -52,7 +51,6 @@ if what in ("gemm", "all"):
 for mode, tag in ((1, "attn_t"), (0, "attn_s")):
     if what not in (tag, "all"):
         continue
-    print(f"env CTC_ATTN_SMALL_HPC={os.environ.get('CTC_ATTN_SMALL_HPC', '2')}")
     inner = heads * 32
     q, kv = rnd(R, inner, dtype=bf), rnd(R, 2 * inner, dtype=bf)
     qs, ks = torch.ones(32, device=dev), torch.ones(32, device=dev)
