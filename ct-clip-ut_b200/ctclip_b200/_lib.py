@@ -63,7 +63,8 @@ SIGNATURES = {
     "ctc_occlusion_heatmap": [P, P, I, I, I, I, I, I, I, I, I, I, I, I, P, P],
 }
 OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, []),
-                 "ctc_launch_count": (ctypes.c_longlong, []), "ctc_vq_num_candidates": (c_int, [c_int])}
+                 "ctc_launch_count": (ctypes.c_longlong, []), "ctc_vq_num_candidates": (c_int, [c_int]),
+                 "ctc_attention_set_tc_bwd": (c_int, [c_int])}
 
 EPI_BF16, EPI_F32, EPI_ARGMAX, EPI_GEGLU, EPI_GEGLU_BWD = 0, 1, 2, 3, 4
 GEMM_TCGEN05, GEMM_SIMT = 0, 1

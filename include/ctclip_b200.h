@@ -114,6 +114,9 @@ int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, const void* v, 
 int ctc_attention_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int B, int T, int H,
                          int W, int heads, const float* q_scale, const float* k_scale, float scale,
                          const float* bias_table, float score_bound, void* o, float* lse, void* stream);
+/* Opt-in: compute dQ of the spatial backward on tcgen05 / TMEM as well (same result to bf16 rounding; measured
+ * 4 % slower than the mma.sync kernel, so off by default).  Returns the previous setting (NOT a status code). */
+int ctc_attention_set_tc_bwd(int on);
 int ctc_attention_score_bound(const float* q_scale, const float* k_scale, float scale, const float* bias_table,
                               int heads, int H, int W, float* bound_dev, void* stream);
 /* Input gradients of the above (through softmax, l2norm and q/k scales). dq bf16 [R,heads*32] (lddq),

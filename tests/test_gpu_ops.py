@@ -219,6 +219,20 @@ def _attn_ref(q, kv, qs, ks, scale, bias, B, T, H, W, heads, mode):
                                                 (1, 2, 6, 6, 6, 2), (0, 1, 1, 10, 10, 4), (0, 1, 3, 8, 8, 2),
                                                 (0, 2, 1, 16, 8, 1)])
 def test_attention_fwd_bwd_probs(lib, mode, B, T, H, W, heads):
+    _attention_fwd_bwd_probs(lib, mode, B, T, H, W, heads)
+
+
+@pytest.mark.parametrize("B,T,H,W,heads", [(1, 2, 24, 24, 8), (1, 3, 8, 8, 2), (2, 1, 16, 8, 1)])
+def test_attention_bwd_dq_on_tcgen05(lib, B, T, H, W, heads):
+    """Same checks with dQ computed by the opt-in tcgen05 / TMEM kernel (ctc_attention_set_tc_bwd)."""
+    prev = lib.load().ctc_attention_set_tc_bwd(1)
+    try:
+        _attention_fwd_bwd_probs(lib, 0, B, T, H, W, heads)
+    finally:
+        lib.load().ctc_attention_set_tc_bwd(prev)
+
+
+def _attention_fwd_bwd_probs(lib, mode, B, T, H, W, heads):
     if mode == 1 and not (T == H == W):
         pytest.skip("temporal mode uses T tokens")
     R, inner = B * T * H * W, heads * 32
