@@ -1,0 +1,76 @@
+"""GPU: the drop-in module surface end to end — `utils.CTClipInference.CTClipInference` +
+`utils.visualizations.Visualizations` imported the way `src/inference_ctclip.py:5-7` imports them, driven with a
+stand-in text tower / tokenizer / dataset, must run all five attribution methods and write the reference's `.npy`
+names (visualizations.py:638-639, 848-849, 906, 1021-1026, 1082)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctclip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeTokens(dict):
+    def to(self, device):
+        return FakeTokens({k: v.to(device) for k, v in self.items()})
+
+
+class FakeTokenizer:
+    def __call__(self, texts, **kw):
+        n = len(texts) if isinstance(texts, (list, tuple)) else 1
+        return FakeTokens(input_ids=torch.arange(n * 4).view(n, 4))
+
+
+class FakeTextTower(torch.nn.Module):
+    def __init__(self, dim_text):
+        super().__init__()
+        self.emb = torch.nn.Embedding(64, dim_text)
+
+    def forward(self, input_ids):
+        return SimpleNamespace(last_hidden_state=self.emb(input_ids % 64))
+
+
+def test_inference_entry_point_writes_reference_outputs(tmp_path):
+    from models.ctclip import CTCLIP                       # the import names of src/inference_ctclip.py:5-7
+    from utils.ctvit import CTViT
+    from utils.CTClipInference import CTClipInference
+    cfg = O.TINY
+    torch.manual_seed(0)
+    vit = CTViT(dim=cfg.dim, codebook_size=cfg.codebook_size, image_size=cfg.image_size, patch_size=cfg.patch_size,
+                temporal_patch_size=cfg.temporal_patch_size, spatial_depth=cfg.spatial_depth,
+                temporal_depth=cfg.temporal_depth, dim_head=cfg.dim_head, heads=cfg.heads)
+    T, H = cfg.depth_voxels // cfg.temporal_patch_size, cfg.image_size // cfg.patch_size
+    clip = CTCLIP(text_encoder=FakeTextTower(cfg.dim_text), image_encoder=vit, dim_text=cfg.dim_text,
+                  dim_image=H * H * cfg.dim, dim_latent=cfg.dim_latent)
+    vol = O.synthetic_volume(cfg, 0)[0]                    # [1, D, H, W] like the dataset's samples
+    labels = torch.zeros(18)
+    sample = (vol, "no acute findings", labels, "scan0", "scan0.nii.gz")
+    dataset = [sample]
+    loader = [(vol.unsqueeze(0), ["no acute findings"], labels.unsqueeze(0), ["scan0"], ["scan0.nii.gz"])]
+    inf = CTClipInference(clip, batch_size=1, dataset=dataset, dataloader=loader, tokenizer=FakeTokenizer(),
+                          results_folder=tmp_path)
+    vis = inf.vis
+    vis.visualize(raw_attention_maps=True, attention_rollout=True, integrated_gradients=True, grad_cam=True)
+    D, Hh, Ww = vol.shape[-3:]
+    tokens = FakeTokenizer()(["no acute findings"]).to("cuda")
+    vis.visualize_occlusion_sensitivity(vol.unsqueeze(0).cuda(), tokens, labels, "scan0", "scan0.nii.gz",
+                                        patch_size=(4, 8, 8), stride=(2, 4, 4))
+    root = inf.results_folder
+
+    def load(rel):
+        f = list(root.glob(rel))
+        assert len(f) == 1, (rel, [str(p) for p in root.rglob("*.npy")])
+        return np.load(f[0], allow_pickle=True)
+
+    assert load("raw_attention_grids/1/scan0_spatial_grid.npy").ndim >= 3
+    assert load("raw_attention_grids/1/scan0_temporal_grid.npy").ndim >= 3
+    for name in ("attention_rollout/1/scan0_spatial.npy", "attention_rollout/1/scan0_temporal.npy",
+                 "integrated_gradients/1/scan0.npy", "occlusion/1/scan0__heatmap.npy",
+                 *[f"grad_cam/1/scan0_{k}.npy" for k in ("spatial_ff", "temporal_ff", "spatial", "temporal", "combined", "vq")]):
+        a = load(name)
+        assert a.shape == (D, Ww, Hh) and a.dtype == np.float32 and np.isfinite(a).all(), (name, a.shape)
+    # every map is normalised to [0, 1] by its reference recipe
+    assert 0.0 <= float(load("occlusion/1/scan0__heatmap.npy").min()) and float(load("occlusion/1/scan0__heatmap.npy").max()) <= 1.0
