@@ -4,8 +4,9 @@
 // never materialised:
 //   - integrated gradients:  x' = 1 + alpha * (x - 1)          (visualizations.py:853-862)
 //   - occlusion:             x'[cube] = -1                      (visualizations.py:380-381)
-// HBM-bound: the fp32 volume is read exactly once with 128-bit coalesced loads (a CTA owns a
-// group of G patches that are adjacent along W, i.e. pt*p1 contiguous runs of G*p2 floats),
+// HBM-bound: the fp32 volume is read exactly once — a CTA owns a group of G patches that are adjacent
+// along W and fetches its [pt][p1][G*p2] box with ONE 4-D TMA load (cp.async.bulk.tensor over the
+// [B, D, H, W] volume; cp.async 16-byte copies only when the geometry does not fit a tensor map) —
 // staged in shared memory, normalised with fp32 two-pass statistics (near-constant "air" patches
 // have rstd up to ~316, so the statistics must not be taken in bf16) and written once as the
 // bf16 A-operand of the patch-embedding GEMM.
@@ -106,12 +107,30 @@ CTC_DEVINL void load_tile_async(float* tile, const float* vb, const PatchGeom& g
     }
 }
 
+// one elected thread issues the TMA box load of the CTA's volume tile; everybody waits on the mbarrier
+CTC_DEVINL void load_tile_tma(float* tile, const CUtensorMap* tmap, uint64_t* bar, const PatchGeom& g, int b, int tp,
+                              int hp, int x0, int rows, int rowlen) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, (uint32_t)(rows * rowlen * 4));
+        tma_load_4d(tile, tmap, bar, x0, hp * g.p, tp * g.pt, g.vol_stride ? b : 0);
+    }
+    mbar_wait(bar, 0);
+}
+
+template <bool TMA>
 __global__ void __launch_bounds__(256)
-patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float eps, const float* __restrict__ alpha,
-                       const int* __restrict__ occl, float oval, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float tile[];
+patchify_ln_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ vol, PatchGeom g,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                       const float* __restrict__ alpha, const int* __restrict__ occl, float oval,
+                       __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(128) float tile[];
     __shared__ float s_mean[32], s_rstd[32], s_part[512];
+    __shared__ uint64_t tma_bar;
     const int groups_w = g.Wp / g.G;
     int bid = blockIdx.x;
     const int gw = bid % groups_w; bid /= groups_w;
@@ -125,9 +144,13 @@ patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
     const float a = has_alpha ? alpha[b] : 1.f;
     const int* oc = occl ? occl + b * 6 : nullptr;
     const int x0 = gw * rowlen;
-    load_tile_async(tile, vb, g, tp, hp, x0, rows, rowlen);
-    cp_async_wait_all();
-    __syncthreads();
+    if (TMA) {
+        load_tile_tma(tile, &tmap, &tma_bar, g, b, tp, hp, x0, rows, rowlen);
+    } else {
+        load_tile_async(tile, vb, g, tp, hp, x0, rows, rowlen);
+        cp_async_wait_all();
+        __syncthreads();
+    }
     // ---- perturbations applied in shared memory (only when requested / when the cube touches this tile)
     bool hit = false;
     if (oc && oc[3] > 0) {
@@ -169,12 +192,15 @@ patchify_ln_fwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
 // Backward: dx' = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dY * gamma;  chain through
 // x' = 1 + alpha (x - 1) is NOT applied: IG differentiates w.r.t. the interpolated input itself
 // (visualizations.py:863,872).  The occlusion path is forward only.
+template <bool TMA>
 __global__ void __launch_bounds__(256)
-patchify_ln_bwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* __restrict__ gamma, float eps,
-                       const float* __restrict__ alpha, const __nv_bfloat16* __restrict__ dy,
-                       float* __restrict__ grad, int sum_over_batch, float wscale) {
-    extern __shared__ float tile[];
+patchify_ln_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ vol, PatchGeom g,
+                       const float* __restrict__ gamma, float eps, const float* __restrict__ alpha,
+                       const __nv_bfloat16* __restrict__ dy, float* __restrict__ grad, int sum_over_batch,
+                       float wscale) {
+    extern __shared__ __align__(128) float tile[];
     __shared__ float s_mean[32], s_rstd[32], s_part[512], s_mg[32], s_mgx[32];
+    __shared__ uint64_t tma_bar;
     const int groups_w = g.Wp / g.G;
     int bid = blockIdx.x;
     const int gw = bid % groups_w; bid /= groups_w;
@@ -189,12 +215,13 @@ patchify_ln_bwd_kernel(const float* __restrict__ vol, PatchGeom g, const float* 
     const int x0 = gw * rowlen;
     const long long tok0 = (((long long)b * g.T + tp) * g.Hp + hp) * g.Wp + (long long)gw * g.G;
     __nv_bfloat16* dys = reinterpret_cast<__nv_bfloat16*>(tile + rows * rowlen);   // [G][P] bf16 (contiguous in global)
-    load_tile_async(tile, vb, g, tp, hp, x0, rows, rowlen);
+    if (!TMA) load_tile_async(tile, vb, g, tp, hp, x0, rows, rowlen);
     {
         const int n16 = g.G * g.P / 8;                      // the CTA's G patches are adjacent rows of dY
         const __nv_bfloat16* src = dy + tok0 * g.P;
         for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async_16(dys + i * 8, src + i * 8);
     }
+    if (TMA) load_tile_tma(tile, &tmap, &tma_bar, g, b, tp, hp, x0, rows, rowlen);
     cp_async_wait_all();
     __syncthreads();
     if (has_alpha) {
@@ -280,6 +307,35 @@ static int make_geom(PatchGeom& g, long long vol_stride, int B, int D, int H, in
     return 0;
 }
 
+typedef CUresult (*PFN_encodeTiledP)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 4-D tensor map over the fp32 volume(s) [Bv, D, H, W] with box [1, pt, p, G*p]; false when the geometry does not fit
+static bool make_volume_tmap(CUtensorMap* map, const float* vol, const PatchGeom& g) {
+    static PFN_encodeTiledP enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return false;
+        enc = reinterpret_cast<PFN_encodeTiledP>(p);
+    }
+    const int rowlen = g.G * g.p;
+    if (rowlen > 256 || g.p > 256 || g.pt > 256 || (rowlen * 4) % 16 != 0 || (g.W * 4) % 16 != 0 ||
+        (reinterpret_cast<uintptr_t>(vol) & 15) != 0 || (g.vol_stride && (g.vol_stride * 4) % 16 != 0))
+        return false;
+    const long long vs = g.vol_stride ? g.vol_stride : (long long)g.D * g.H * g.W;
+    cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.D, (cuuint64_t)(g.vol_stride ? g.B : 1)};
+    cuuint64_t strides[3] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.H * g.W * 4, (cuuint64_t)vs * 4};
+    cuuint32_t box[4] = {(cuuint32_t)rowlen, (cuuint32_t)g.p, (cuuint32_t)g.pt, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(vol), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace ctc
 
 using namespace ctc;
@@ -292,14 +348,22 @@ extern "C" int ctc_patchify_ln_fwd(const float* volume, int64_t vol_batch_stride
     const size_t smem = (size_t)g.G * g.P * 4;
     static size_t configured = 0;
     if (smem > configured) {
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            (int)cudaSharedmemCarveoutMaxShared));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             (int)cudaSharedmemCarveoutMaxShared));
         configured = smem;
     }
     const long long grid = (long long)B * g.T * g.Hp * (g.Wp / g.G);
-    patchify_ln_fwd_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
-        volume, g, gamma, beta, eps, alpha, occl, occl_value, (__nv_bfloat16*)out_bf16);
+    CUtensorMap tmap{};
+    if (make_volume_tmap(&tmap, volume, g))
+        patchify_ln_fwd_kernel<true><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
+            tmap, volume, g, gamma, beta, eps, alpha, occl, occl_value, (__nv_bfloat16*)out_bf16);
+    else
+        patchify_ln_fwd_kernel<false><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
+            tmap, volume, g, gamma, beta, eps, alpha, occl, occl_value, (__nv_bfloat16*)out_bf16);
     CTC_LAUNCH_CHECK();
     return 0;
 }
@@ -312,14 +376,22 @@ extern "C" int ctc_patchify_ln_bwd(const float* volume, int64_t vol_batch_stride
     const size_t smem = (size_t)g.G * g.P * 6;
     static size_t configured = 0;
     if (smem > configured) {
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            (int)cudaSharedmemCarveoutMaxShared));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             (int)cudaSharedmemCarveoutMaxShared));
         configured = smem;
     }
     const long long grid = (long long)B * g.T * g.Hp * (g.Wp / g.G);
-    patchify_ln_bwd_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
-        volume, g, gamma, eps, alpha, (const __nv_bfloat16*)dy_bf16, grad, sum_over_batch, wscale);
+    CUtensorMap tmap{};
+    if (make_volume_tmap(&tmap, volume, g))
+        patchify_ln_bwd_kernel<true><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
+            tmap, volume, g, gamma, eps, alpha, (const __nv_bfloat16*)dy_bf16, grad, sum_over_batch, wscale);
+    else
+        patchify_ln_bwd_kernel<false><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
+            tmap, volume, g, gamma, eps, alpha, (const __nv_bfloat16*)dy_bf16, grad, sum_over_batch, wscale);
     CTC_LAUNCH_CHECK();
     return 0;
 }
