@@ -165,6 +165,25 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
     torch.cuda.synchronize()
     # headline: EVERY window of the sweep is evaluated.  Second pass: windows that lie entirely in -1 air / padding
     # (no-ops, score == baseline bit for bit) are detected on the device and skipped - reported separately.
+    # the three single-pass methods of the suite (BASELINE.json configs[0] / [4]) on the same volume, rank 0 only:
+    # device compute + trilinear up-sampling to 240x480x480 + D2H of every map the reference saves
+    def single_pass_methods():
+        vol = host_vol.to(dev, non_blocking=True)
+        shape = tuple(vol.shape[-3:])
+        out = {}
+        t0 = time.perf_counter()
+        sp, tp = A.attention_rollout_maps(eng, vol, tl)
+        maps_ = [A.upsample(sp, shape).cpu(), A.upsample(tp, shape).cpu()]
+        torch.cuda.synchronize(); out["attention_rollout_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        cams = A.grad_cam(eng, vol, tl)
+        maps_ += [A.upsample(cams[k], shape).cpu() for k in ("spatial_ff", "temporal_ff", "spatial", "temporal", "combined", "vq")]
+        torch.cuda.synchronize(); out["grad_cam_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        rs, rt = A.raw_attention_maps(eng, vol, tl)
+        maps_ += [rs.cpu(), rt.cpu()]
+        torch.cuda.synchronize(); out["raw_attention_s"] = time.perf_counter() - t0
+        return out
     wall, occ_s, ig_s, n_win, maps, _ = once(False)
     wall2, occ2_s, _, _, maps2, stats = once(True)
     same = bool(torch.equal(maps[0], maps2[0]))
@@ -182,6 +201,7 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
             "with_noop_window_skip": {"seconds_per_volume": wall2, "occlusion_s": occ2_s, "value": 1.0 / wall2,
                                       "windows_evaluated_rank0": stats.get("evaluated"),
                                       "windows_noop_rank0": stats.get("noop"), "heat_map_identical": same},
+            "single_pass_methods_rank0": single_pass_methods(),
             "dense_equiv_pflop": (dense + ig_flop) / 1e15, "executed_pflop": (execd + ig_flop) / 1e15,
             "frac_of_tensor_peak_executed": (execd + ig_flop) / (occ_s + ig_s) / peak,
             "timing": "wall clock incl. H2D of the volume and D2H of both maps, max over ranks; one un-warmed pass "

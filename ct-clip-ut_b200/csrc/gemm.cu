@@ -326,6 +326,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
             }
+            if constexpr (EPI == CTC_EPI_GEGLU_BWD) {
+                // same idea for the saved pre-activation u the adjoint reads (bf16, 2 x this warp's columns per row)
+                const int prow = tm * BM + ew * 32 + lane;
+                const int pcol = 2 * (tn * BN + cbeg);
+                if (prow < g.M) {
+                    const __nv_bfloat16* pu = reinterpret_cast<const __nv_bfloat16*>(g.aux) + (long long)prow * g.ldaux + pcol;
+#pragma unroll
+                    for (int c = 0; c < 2 * kColsPerWarp; c += 64)
+                        if (pcol + c < 2 * g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + c));
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int row = tm * BM + ew * 32 + lane;

@@ -393,8 +393,9 @@ class Engine:
             capture[tag + "_ff"] = dx3.clone()          # d/d(ff output)  == grad of x3
         # ---- FeedForward
         # dh = dx3 @ W2, then the GEGLU adjoint as its own HBM-bound pass.  (A fused GEMM epilogue exists,
-        # EPI_GEGLU_BWD, but four epilogue warps evaluating gelu/gelu' per element made the GEMM 3.6x slower
-        # than GEMM + stand-alone pass on B200 - profiles/r01_geglu_fusion.md - so it is not used.)
+        # EPI_GEGLU_BWD, but evaluating gelu / gelu' per element and re-reading u in the epilogue warps makes the
+        # GEMM epilogue-bound: 779 us fused against 160 + 243 us for GEMM + stand-alone pass on B200 with eight
+        # epilogue warps and the L2 prefetch of u - so it is not used.)
         du = self._empty(R, 2 * FP, dtype=bf)
         if self.fuse_geglu_bwd and self.gemm_impl == _lib.GEMM_TCGEN05:
             self.gemm(dx3_bf, lw.w2_t, du, _lib.EPI_GEGLU_BWD, aux=lc.u)
