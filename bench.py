@@ -154,7 +154,7 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
         e[1].record()
         ig, _ = A.integrated_gradients(eng, vol, tl, steps=50, batch=5)
         e[2].record()
-        out = (heat.cpu(), ig.cpu())
+        out = (A.to_host(heat, 0), A.to_host(ig, 1))               # both maps on the host (pinned staging buffers)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         return (wall, e[0].elapsed_time(e[1]) / 1e3, e[1].elapsed_time(e[2]) / 1e3, int(aux["included"].sum()), out,
@@ -185,6 +185,7 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
         torch.cuda.synchronize(); out["raw_attention_s"] = time.perf_counter() - t0
         return out
     wall, occ_s, ig_s, n_win, maps, _ = once(False)
+    maps = tuple(m.clone() for m in maps)            # the pinned staging buffers are re-used by the next pass
     wall2, occ2_s, _, _, maps2, stats = once(True)
     same = bool(torch.equal(maps[0], maps2[0]))
     t = torch.tensor([wall, occ_s, ig_s, wall2, occ2_s], device=dev)
