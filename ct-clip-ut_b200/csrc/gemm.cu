@@ -355,9 +355,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     tmem_ld_32x32b_x32(taddr + c, v);
                     tmem_ld_wait();
                     const int col0 = tn * BN + c;
+                    // groups of 4 consecutive codes: only the group maximum enters the top-2 tracker (11 ALU ops per
+                    // 4 scores instead of 32); the recorded index is the group's first code and vq_refine re-scores all
+                    // four codes of a candidate group in fp32
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (full || col0 + j < g.N) t2[j & 3].push(__uint_as_float(v[j]), col0 + j);
+                    for (int j = 0; j < 32; j += 4) {
+                        float m;
+                        if (full || col0 + j + 3 < g.N) {
+                            m = fmaxf(fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                      fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                        } else {
+                            m = -3.0e38f;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col0 + j + e < g.N) m = fmaxf(m, __uint_as_float(v[j + e]));
+                        }
+                        t2[(j >> 2) & 3].push(m, col0 + j);
+                    }
                 }
 #pragma unroll
                 for (int i = 1; i < 4; ++i) { t2[0].push(t2[i].v0, t2[i].i0); t2[0].push(t2[i].v1, t2[i].i1); }

@@ -7,13 +7,14 @@
 namespace ctc {
 
 // ---------------------------------------------------------------------------------------------
-// VQ refine: the bf16 tensor-core GEMM (epilogue ARGMAX) leaves per row the top-2 scores of every
-// 256-code tile.  Candidates whose bf16 score is within a rounding margin of the best are
-// re-scored exactly in fp32 (x_fp32 . E_fp32), so the selected code equals the fp32 arg-max of the
-// reference (ties -> lowest index, as torch.argmax).  One warp per row.
+// VQ refine: the bf16 tensor-core GEMM (epilogue ARGMAX) leaves per row, for every 128-code slice, the two best
+// GROUPS of four consecutive codes (group maximum + first code of the group).  Every code of a candidate group
+// whose bf16 maximum is within a rounding margin of the best is re-scored exactly in fp32 (x_fp32 . E_fp32), so
+// the selected code equals the fp32 arg-max of the reference (ties -> lowest index, as torch.argmax).
+// One warp per row.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-vq_refine_kernel(const float* __restrict__ x, int R, int C, const float* __restrict__ codebook,
+vq_refine_kernel(const float* __restrict__ x, int R, int C, const float* __restrict__ codebook, int K,
                  const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int n_cand,
                  int* __restrict__ ind) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -41,16 +42,18 @@ vq_refine_kernel(const float* __restrict__ x, int R, int C, const float* __restr
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
-            const int code = __shfl_sync(0xffffffffu, (c < n_cand) ? cand_idx[(long long)row * n_cand + c] : 0, src);
-            const float* e = codebook + (long long)code * C;
-            float d = 0.f;
-            for (int k = lane * 4; k < C; k += 128) {
-                const float4 a = *reinterpret_cast<const float4*>(xr + k);
-                const float4 b = *reinterpret_cast<const float4*>(e + k);
-                d += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+            const int code0 = __shfl_sync(0xffffffffu, (c < n_cand) ? cand_idx[(long long)row * n_cand + c] : 0, src);
+            for (int code = code0; code < min(code0 + 4, K); ++code) {
+                const float* e = codebook + (long long)code * C;
+                float d = 0.f;
+                for (int k = lane * 4; k < C; k += 128) {
+                    const float4 a = *reinterpret_cast<const float4*>(xr + k);
+                    const float4 b = *reinterpret_cast<const float4*>(e + k);
+                    d += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+                }
+                d = warp_sum(d);
+                if (d > best_exact || (d == best_exact && code < best_idx)) { best_exact = d; best_idx = code; }
             }
-            d = warp_sum(d);
-            if (d > best_exact || (d == best_exact && code < best_idx)) { best_exact = d; best_idx = code; }
         }
     }
     if (lane == 0) ind[row] = best_idx;
@@ -416,7 +419,7 @@ extern "C" int ctc_vq_argmax(const float* x, const void* x_bf16, int R, int C, c
     if (int e = gemm_bf16(x_bf16, C, codebook_bf16, C, nullptr, 0, R, K, C, CTC_EPI_ARGMAX, nullptr, nullptr, 0, nullptr, 0,
                           cand_val, cand_idx, CTC_GEMM_TCGEN05, (cudaStream_t)stream))
         return e;
-    vq_refine_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, R, C, codebook, cand_val, cand_idx,
+    vq_refine_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, R, C, codebook, K, cand_val, cand_idx,
                                                                     n_cand, ind);
     CTC_LAUNCH_CHECK();
     return 0;

@@ -143,9 +143,10 @@ int ctc_cpb_table(const float* w0, const float* b0, const float* w1, const float
                   const float* b2, int dim, int heads, int H, int W, float* table, void* stream);
 
 /* VQ nearest-code search (ctvit.py:117-118; vector_quantize_pytorch cosine codebook):
- * cand_val/cand_idx [R, ctc_vq_num_candidates(K)] scratch = top-2 of every 128-code slice of the bf16
- * score GEMM (ctc_gemm_bf16 epi ARGMAX is run internally); candidates within a rounding margin of the
- * best are re-scored in fp32 against the fp32 codebook, so the arg-max is exact w.r.t. x.  ind int32 [R]. */
+ * cand_val/cand_idx [R, ctc_vq_num_candidates(K)] scratch = the two best groups of 4 consecutive codes of every
+ * 128-code slice of the bf16 score GEMM (ctc_gemm_bf16 epi ARGMAX is run internally); every code of a group within
+ * a rounding margin of the best is re-scored in fp32 against the fp32 codebook, so the arg-max is exact w.r.t. x.
+ * ind int32 [R]. */
 int ctc_vq_num_candidates(int K);
 int ctc_vq_argmax(const float* x, const void* x_bf16, int R, int C, const float* codebook,
                   const void* codebook_bf16, int K, float* cand_val, int* cand_idx, int* ind, void* stream);
