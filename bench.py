@@ -350,6 +350,13 @@ def run_product(args):
     if rank == 0:
         sampler.stop_flag.set()
     e2e_val = BATCH * world / e2e_s
+    # the e2e step moves 1.77 GB of fp32 voxels per rank over PCIe: measure this box's pinned H2D rate alone so the
+    # bound is visible next to the number (it ranged from 8 to 55 GB/s across the boxes of this pool)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    bufs[0].copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbps = host.numel() * 4 / (time.perf_counter() - t0) / 1e9
     e2e_diff = float((res[:BATCH].to(dev) - sim_graph.flatten()).abs().max())
     if e2e_diff > 1e-6:
         print(f"[rank {rank}] e2e vs graph logits differ by {e2e_diff:.3e}\n  e2e   {res[:BATCH].tolist()}\n  graph "
@@ -420,7 +427,9 @@ def run_product(args):
         "model_tflops": step_flops * world / (ms_step / 1e3) / 1e12,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4 * world,
                 "d2h_bytes_per_step": int(res.numel() * 4) * world,
-                "api": "CTCLIP.forward + sim.backward(), H2D of step i+1 overlapped with compute of step i"},
+                "api": "CTCLIP.forward + sim.backward(), H2D of step i+1 overlapped with compute of step i",
+                "h2d_gbps_this_box": h2d_gbps,
+                "bound": "PCIe: max(compute, H2D of the 1.77 GB fp32 batch per rank); compute alone is ms_per_step"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": sampler.summary(),
