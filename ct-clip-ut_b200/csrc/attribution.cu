@@ -321,9 +321,27 @@ patch_is_constant_kernel(const float* __restrict__ vol, int D, int H, int W, int
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) flags[blockIdx.x] = bad ? 0 : 1;
 }
+
+// Zero-shot scoring: sim [B, 2P] holds (present, absent) logit pairs; out[b, j] = softmax(pair)[0] as float64.
+__global__ void pair_softmax_kernel(const float* __restrict__ sim, int n, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // softmax([a, b])[0] = 1 / (1 + e^(b-a)), evaluated in double and rounded to the reference's fp32 result type
+    const double d = (double)sim[2 * i + 1] - (double)sim[2 * i];
+    out[i] = (double)(float)(1.0 / (1.0 + exp(d)));
+}
 }  // namespace ctc
 
 using namespace ctc;
+
+extern "C" int ctc_pair_softmax(const float* sim, int B, int P, double* out, void* stream) {
+    CTC_REQUIRE(B >= 0 && P >= 0, "pair_softmax: B=%d P=%d", B, P);
+    const int n = B * P;
+    if (n == 0) return 0;
+    pair_softmax_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sim, n, out);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int ctc_patch_is_constant(const float* volume, int D, int H, int W, int pt, int p, float value,
                                      unsigned char* flags, void* stream) {

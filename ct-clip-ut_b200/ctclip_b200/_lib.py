@@ -57,6 +57,7 @@ SIGNATURES = {
                           ctypes.c_double, I, I, I, F, P, P, P],
     "ctc_minmax": [P, L, P, P],
     "ctc_patch_is_constant": [P, I, I, I, I, I, F, P, P],
+    "ctc_pair_softmax": [P, I, I, P, P],
     "ctc_normalize": [P, I, I, I, P, I, I, P, P],
     "ctc_hist16": [P, L, I, ctypes.c_uint, P, P],
     "ctc_ig_finalize": [P, I, I, I, F, F, F, F, I, P, P],

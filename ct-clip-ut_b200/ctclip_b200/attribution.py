@@ -444,7 +444,7 @@ class Visualizations:
     (matplotlib, :427-567) is out of scope: overlays are skipped, arrays are always saved."""
 
     def __init__(self, model, accelerator, dataset, dist_dataloader, batch_size, results_folder, diff_embeds_folder,
-                 tokenizer, window_batch: int = 8, ig_batch: int = 5, parity_sharding: bool = True):
+                 tokenizer, window_batch: int = 8, ig_batch: int = 10, parity_sharding: bool = True):
         self.model = model.module if hasattr(model, "module") else model
         self.accelerator = accelerator
         self.dataset, self.dist_dataloader, self.batch_size = dataset, dist_dataloader, batch_size

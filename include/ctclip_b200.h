@@ -209,6 +209,9 @@ int ctc_preprocess_ct(const void* raw, int raw_dtype, int H0, int W0, int D0, in
                       double target_xy, int D, int H, int W, float pad_value, float* out, int* resampled_dhw,
                       void* stream);
 int ctc_minmax(const float* x, int64_t n, float* mm, void* stream);
+/* Zero-shot scoring (CTClipInference.py:133-145, 171-180): sim fp32 [B, 2P] with the "There is X." logit at
+ * column 2j and the "There is no X." logit at 2j+1; out float64 [B, P] = softmax over each pair, first entry. */
+int ctc_pair_softmax(const float* sim, int B, int P, double* out, void* stream);
 /* flags uint8 [D/pt, H/p, W/p]: 1 iff every voxel of the patch equals `value`.  An occlusion window made only of
  * such patches leaves the volume unchanged: its score is the un-occluded score (visualizations.py:380-390). */
 int ctc_patch_is_constant(const float* volume, int D, int H, int W, int pt, int p, float value, unsigned char* flags,

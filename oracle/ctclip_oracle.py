@@ -637,3 +637,21 @@ def occlusion_scores(image: Tensor, text_embeds: Tensor, sd, cfg: CTConfig, wind
             occ = occlusion_mask_apply(image, win, patch_size)
             scores.append(float(ctclip_forward(occ, text_embeds, sd, cfg)[0][0, 0]))
     return orig, scores
+
+
+# --------------------------------------------------------------------------- #
+# zero-shot scoring  (src/utils/CTClipInference.py)                           #
+# --------------------------------------------------------------------------- #
+def zero_shot_predictions(image_latents: Tensor, pair_latents: Tensor, temp: Tensor, rank: int = 0) -> Tensor:
+    """CTClipInference.validate_prompts + the scoring lines of zeroshot (CTClipInference.py:133-145, 171-180)
+    for ONE sample and P pathologies.  `pair_latents` [P,2,d]: row 0 = "There is X.", row 1 = "There is no X."
+    (the tokenizer call at :159-165 puts them at even / odd rows, split at :137-138).  Per pathology:
+    present = (il @ tl_present.T * temp).diag()[rank], absent likewise, p = softmax([present, absent])[0],
+    stored into a float64 vector (:156, 180).  Returns float64 [P]."""
+    out = torch.zeros(pair_latents.shape[0], dtype=torch.double)
+    for j in range(pair_latents.shape[0]):
+        tl = pair_latents[j]
+        present = torch.diag(image_latents @ tl[0::2].t() * temp)[rank]
+        absent = torch.diag(image_latents @ tl[1::2].t() * temp)[rank]
+        out[j] = torch.softmax(torch.stack([present, absent]), dim=0)[0]
+    return out
