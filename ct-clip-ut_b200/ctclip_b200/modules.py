@@ -205,12 +205,20 @@ class _SimFunction(torch.autograd.Function):
                              want_tokens=want_tokens)
         fctx.engine, fctx.ectx = engine, ctx
         holder["ctx"] = ctx
-        fctx.mark_non_differentiable(ctx.image_latents)
-        return ctx.sim, ctx.image_latents
+        # Fresh output tensors: returning ctx.sim itself would close a reference cycle through the autograd node
+        # (sim -> grad_fn -> fctx.ectx -> ctx.sim) that keeps ~1.4 GB of saved activations per volume alive until a
+        # cyclic GC pass, and the caching allocator then grows by a full context every step.
+        sim, il = ctx.sim.clone(), ctx.image_latents.clone()
+        fctx.mark_non_differentiable(il)
+        return sim, il
 
     @staticmethod
     def backward(fctx, gsim, _gil):
+        if fctx.ectx is None:
+            raise RuntimeError("CTCLIP: the saved activations were released by the first backward pass "
+                               "(a second backward through the same forward is not supported)")
         grad = fctx.engine.backward(fctx.ectx, gsim=gsim)
+        fctx.ectx = None                 # saved activations are released with the last outside reference to the Ctx
         return grad, None, None, None, None
 
 
@@ -263,6 +271,7 @@ class CTCLIP(nn.Module):
     def forward(self, text_inputs, image_inputs, text_embeds=None):
         """Returns (sim_matrix, image_latents, text_latents, temperature.exp(), image_tokens) — ctclip.py:99-129."""
         eng = self.engine(image_inputs.device)
+        self.last_ctx = None             # drop the previous call's saved activations before allocating this call's
         if text_inputs:
             text_output = self.text_transformer(**text_inputs).last_hidden_state[:, 0, :]
         else:

@@ -74,3 +74,45 @@ def test_inference_entry_point_writes_reference_outputs(tmp_path):
         assert a.shape == (D, Ww, Hh) and a.dtype == np.float32 and np.isfinite(a).all(), (name, a.shape)
     # every map is normalised to [0, 1] by its reference recipe
     assert 0.0 <= float(load("occlusion/1/scan0__heatmap.npy").min()) and float(load("occlusion/1/scan0__heatmap.npy").max()) <= 1.0
+
+
+def test_module_forward_backward_does_not_leak():
+    """CTCLIP.forward + sim.backward() in a loop (the bench's end-to-end step, the reference's IG / Grad-CAM call
+    pattern visualizations.py:862-872): device memory must be flat from the second step on WITHOUT relying on the
+    cyclic garbage collector, and a second backward through a released forward must fail loudly."""
+    import gc
+    from models.ctclip import CTCLIP
+    from utils.ctvit import CTViT
+    cfg = O.TINY
+    torch.manual_seed(0)
+    vit = CTViT(dim=cfg.dim, codebook_size=cfg.codebook_size, image_size=cfg.image_size, patch_size=cfg.patch_size,
+                temporal_patch_size=cfg.temporal_patch_size, spatial_depth=cfg.spatial_depth,
+                temporal_depth=cfg.temporal_depth, dim_head=cfg.dim_head, heads=cfg.heads)
+    H = cfg.image_size // cfg.patch_size
+    clip = CTCLIP(text_encoder=torch.nn.Identity(), image_encoder=vit, dim_text=cfg.dim_text,
+                  dim_image=H * H * cfg.dim, dim_latent=cfg.dim_latent).cuda()
+    vol = O.synthetic_volume(cfg, 0, batch=2).cuda()
+    text = O.synthetic_text_embeds(cfg, 7).cuda()
+    gc.collect()
+    gc.disable()
+    try:
+        used, g0, same = [], None, []
+        for _ in range(5):
+            x = vol.clone().requires_grad_()
+            sim, *_ = clip(None, x, text)
+            sim[:, 0].sum().backward()
+            if g0 is None:
+                g0 = x.grad.clone()
+            same.append(bool(torch.equal(g0, x.grad)))
+            del x, sim, _
+            torch.cuda.synchronize()
+            used.append(torch.cuda.memory_allocated())
+    finally:
+        gc.enable()
+    assert used[1] == used[2] == used[3] == used[4], used
+    assert all(same)
+    x = vol.clone().requires_grad_()
+    sim, *_ = clip(None, x, text)
+    sim[:, 0].sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="released"):
+        sim[:, 0].sum().backward()
