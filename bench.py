@@ -144,6 +144,7 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
     NCCL.  End to end: the timed region starts from the pinned host volume and ends with both maps on the host."""
     import torch
     from ctclip_b200 import attribution as A
+    rank = dist.get_rank() if world > 1 else 0
 
     def once(skip_noop):
         t0 = time.perf_counter()
@@ -154,7 +155,9 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
         e[1].record()
         ig, _ = A.integrated_gradients(eng, vol, tl, steps=50, batch=10)
         e[2].record()
-        out = (A.to_host(heat, 0), A.to_host(ig, 1))               # both maps on the host (pinned staging buffers)
+        # both maps on the host (pinned staging buffers) - on rank 0, the process that saves them
+        # (visualizations.py:411-424, 903-906); the other ranks only finish their device work
+        out = (A.to_host(heat, 0), A.to_host(ig, 1)) if rank == 0 else (heat, ig)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         return (wall, e[0].elapsed_time(e[1]) / 1e3, e[1].elapsed_time(e[2]) / 1e3, int(aux["included"].sum()), out,
@@ -168,6 +171,9 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
     # one untimed IG batch: the first batch of 10 alpha steps makes the caching allocator cudaMalloc ~15 GB of
     # activation buffers (0.8 s), which a service attributing a stream of volumes pays once, not per volume
     A.integrated_gradients(eng, host_vol.to(dev), tl, steps=10, batch=10, shard_steps=False)
+    # ... and one untimed batch of 32 occlusion windows, for the same reason (compact-frame buffers of the fast path)
+    A.occlusion_scores(eng, host_vol.to(dev), tl, A.occlusion_windows(tuple(host_vol.shape[-3:]))[:32], (20, 40, 40),
+                       skip_noop=False)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
