@@ -534,7 +534,7 @@ class Visualizations:
                                           self._text_latents(text_tokens, text_embeds), patch_size, stride,
                                           self.window_batch, self.parity_sharding, threshold)
         self.saved_outputs["occlusion"] = aux
-        return heat.cpu().numpy() if self.accelerator.is_main_process else None
+        return to_host(heat).numpy() if self.accelerator.is_main_process else None   # view of the pinned staging buffer
 
     def visualize_occlusion_sensitivity(self, image, text_tokens, labels, scan_name, original_scan_path,
                                         patch_size=(20, 40, 40), stride=(10, 20, 20), use_text_embeds=False, prompt=""):
