@@ -56,6 +56,16 @@ def shard_range(total: int, rank: int, world: int, parity: bool = True) -> Tuple
     return start, start + base + (1 if rank < rem else 0)
 
 
+def shard_indices(total: int, rank: int, world: int, parity: bool = True) -> np.ndarray:
+    """Window indices this rank evaluates.  The SET of evaluated windows is the reference's: with parity=True the
+    first (total // world) * world windows (visualizations.py:351-361 truncates the list, then hands out contiguous
+    chunks), else all of them.  Which rank evaluates which window does not enter any result (scores are independent
+    and combined by index), so the windows are dealt round-robin: contiguous chunks give the ranks that own the
+    first / last depth slabs only padding windows (no-ops) and clipped changed-frame sets, and the others wait."""
+    n = (total // world) * world if parity else total
+    return np.arange(rank, n, world, dtype=np.int64)
+
+
 def _world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -248,6 +258,21 @@ def combine_sharded(local: torch.Tensor, start: int, end: int, total: int) -> Tu
     return scores, included
 
 
+def combine_indexed(local: torch.Tensor, idx: np.ndarray, total: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """combine_sharded for an arbitrary (disjoint across ranks) index set per rank: local [len(idx)] or
+    [len(idx), P] -> scores [total(, P)] + included mask [total]."""
+    scores = torch.zeros((total, *local.shape[1:]), device=local.device, dtype=torch.float32)
+    included = torch.zeros(total, dtype=torch.int32, device=local.device)
+    if len(idx):
+        ix = torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(local.device)
+        scores[ix] = local.float()
+        included[ix] = 1
+    if _world()[1] > 1:
+        dist.all_reduce(scores)
+        dist.all_reduce(included)
+    return scores, included.to(torch.uint8)
+
+
 def occlusion_sensitivity(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor,
                           patch_size=(20, 40, 40), stride=(10, 20, 20), batch: int = 8, parity_sharding: bool = True,
                           threshold: float = 0.0, rot90: bool = True, reuse: Optional[bool] = None,
@@ -257,11 +282,11 @@ def occlusion_sensitivity(engine: Engine, volume: torch.Tensor, text_latents: to
     rank, world = _world()
     D, H, W = volume.shape[-3:]
     windows = occlusion_windows((D, H, W), patch_size, stride)
-    start, end = shard_range(len(windows), rank, world, parity_sharding)
+    idx = shard_indices(len(windows), rank, world, parity_sharding)
     stats: dict = {}
-    orig, local = occlusion_scores(engine, volume, text_latents, windows[start:end], patch_size, batch, reuse=reuse,
-                                   skip_noop=skip_noop, stats=stats)
-    scores, included = combine_sharded(local, start, end, len(windows))
+    orig, local = occlusion_scores(engine, volume, text_latents, [windows[i] for i in idx], patch_size, batch,
+                                   reuse=reuse, skip_noop=skip_noop, stats=stats)
+    scores, included = combine_indexed(local, idx, len(windows))
     heat = occlusion_heatmap(orig, scores, included, (D, H, W), patch_size, stride, threshold, rot90)
     return heat, {"orig": orig, "scores": scores, "included": included, "windows": windows, "stats": stats}
 
@@ -276,17 +301,14 @@ def occlusion_sensitivity_multi(engine: Engine, volume: torch.Tensor, text_laten
     rank, world = _world()
     D, H, W = volume.shape[-3:]
     windows = occlusion_windows((D, H, W), patch_size, stride)
-    start, end = shard_range(len(windows), rank, world, parity_sharding)
-    orig, local = occlusion_scores(engine, volume, text_latents, windows[start:end], patch_size, batch, reuse=reuse,
-                                   all_prompts=True)
+    idx = shard_indices(len(windows), rank, world, parity_sharding)
+    orig, local = occlusion_scores(engine, volume, text_latents, [windows[i] for i in idx], patch_size, batch,
+                                   reuse=reuse, all_prompts=True)
     P = text_latents.shape[0]
-    heats, all_scores, included = [], [], None
-    for j in range(P):
-        sc, included = combine_sharded(local[:, j].contiguous(), start, end, len(windows))
-        all_scores.append(sc)
-        heats.append(occlusion_heatmap(float(orig[j]), sc, included, (D, H, W), patch_size, stride, threshold, rot90))
-    return heats, {"orig": orig, "scores": torch.stack(all_scores, 1) if P else None, "included": included,
-                   "windows": windows}
+    scores, included = combine_indexed(local, idx, len(windows))            # one exchange for all prompts
+    heats = [occlusion_heatmap(float(orig[j]), scores[:, j].contiguous(), included, (D, H, W), patch_size, stride,
+                               threshold, rot90) for j in range(P)]
+    return heats, {"orig": orig, "scores": scores if P else None, "included": included, "windows": windows}
 
 
 # ------------------------------------------------------------------------------------------- integrated gradients

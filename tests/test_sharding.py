@@ -34,6 +34,22 @@ def test_shard_range_properties(total, world, parity):
         assert max(e - s for s, e in ranges) - min(e - s for s, e in ranges) <= 1
 
 
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 400), st.integers(1, 9), st.booleans())
+def test_shard_indices_cover_the_reference_window_set(total, world, parity):
+    """Round-robin dealing: disjoint, balanced to within one window, and the union is exactly the set of windows the
+    reference evaluates (its truncated list, visualizations.py:351-361) — who evaluates a window is not observable."""
+    A = _attr()
+    parts = [A.shard_indices(total, r, world, parity).tolist() for r in range(world)]
+    flat = sorted(i for p in parts for i in p)
+    assert len(flat) == len(set(flat))
+    windows = list(range(total))
+    ref = sorted(w for r in range(world) for w in O.shard_windows(windows, r, world)) if parity else windows
+    assert flat == ref
+    assert max(map(len, parts)) - min(map(len, parts)) <= (0 if parity else 1)
+    assert all(p == sorted(p) for p in parts)
+
+
 @settings(max_examples=25, deadline=None)
 @given(st.tuples(st.integers(4, 40), st.integers(4, 40), st.integers(4, 40)),
        st.tuples(st.integers(1, 8), st.integers(1, 8), st.integers(1, 8)),
@@ -57,6 +73,13 @@ def _worker(rank, world, port, total, parity, q):
     s, e = A.shard_range(total, rank, world, parity)
     local = torch.arange(s, e, dtype=torch.float32) * 0.5 + 1.0       # stand-in per-window scores
     scores, inc = A.combine_sharded(local, s, e, total)
+    # the round-robin assignment occlusion_sensitivity uses must assemble the same vector and mask
+    idx = A.shard_indices(total, rank, world, parity)
+    scores_rr, inc_rr = A.combine_indexed(torch.from_numpy(idx).float() * 0.5 + 1.0, idx, total)
+    assert torch.equal(scores_rr, scores) and torch.equal(inc_rr, inc)
+    two = torch.stack([torch.from_numpy(idx).float(), -torch.from_numpy(idx).float()], dim=1)     # [n, P=2] (multi-prompt)
+    s2p, _ = A.combine_indexed(two, idx, total)
+    assert s2p.shape == (total, 2) and torch.equal(s2p[:, 0], -s2p[:, 1])
     # IG partial sums: each rank owns a slice of steps, the all-reduce restores the full sum
     s2, e2 = A.shard_range(50, rank, world, False)
     part = torch.tensor([float(sum(range(s2, e2)))])
