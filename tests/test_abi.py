@@ -40,3 +40,26 @@ def test_product_package_never_imports_the_oracle():
     for f in pkg.rglob("*.py"):
         src = f.read_text()
         assert "oracle" not in re.sub(r"#.*", "", src).replace("oracle/", ""), f"{f} references the oracle"
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++ types, extern "C" guarded) and a C program must
+    link against the shared library and reach an entry point without a GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    from ctclip_b200 import _lib
+    _lib.load()
+    so = ROOT / "ct-clip-ut_b200" / "ctclip_b200" / "libctclip_b200.so"
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "ctclip_b200.h"\n'
+                   'int main(void) { printf("%d %s\\n", ctc_version(), ctc_last_error()); return 0; }\n')
+    exe = tmp_path / "abi"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", str(src),
+                        "-o", str(exe), str(so), f"-Wl,-rpath,{so.parent}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[0] == "100", (r.stdout, r.stderr)
