@@ -278,7 +278,7 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing.  The step (186 kernel launches) is captured once in a CUDA graph so that the
+    # ---- device-resident timing.  The step (174 kernel launches) is captured once in a CUDA graph so that the
     #      timed region is free of host launch overhead (it matters when N ranks share one host).
     for _ in range(2):
         step_device()
@@ -453,7 +453,7 @@ def run_product(args):
                    "backward": "input-gradient only (what IG / Grad-CAM run; no weight gradients)",
                    "parallelism": f"volume-sharded dp{world}, no data-path collective",
                    "l2": "inputs (1.77 GB of volumes, >10 GB activations per step) exceed the 126 MB L2",
-                   "cuda_graph": "the 186-launch step is replayed from one CUDA graph in the device-timed region"},
+                   "cuda_graph": f"the {launches_per_step}-launch step is replayed from one CUDA graph in the device-timed region"},
         "model_tflops": step_flops * world / (ms_step / 1e3) / 1e12,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4 * world,
                 "d2h_bytes_per_step": int(res.numel() * 4) * world,
