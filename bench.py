@@ -366,10 +366,10 @@ def run_product(args):
                 res = res_host[(i - 1) % 2].clone()
         res_done[(n - 1) % 2].synchronize()
         return res_host[(n - 1) % 2].clone()
-    run_e2e(2)
+    run_e2e(max(3, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 6))
+    e2e_steps = max(3, min(args.steps, 8))
     res = run_e2e(e2e_steps)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
