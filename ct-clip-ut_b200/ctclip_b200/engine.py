@@ -234,11 +234,18 @@ class Engine:
         (occlusion cubes).  `save` keeps what backward needs; `keep_attn` keeps q/kv/lse only (rollout);
         `keep_stream` keeps the input of every spatial layer and the spatial output (occlusion baseline cache)."""
         cfg, pl = self.cfg, self.plan
-        assert volume.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous()
+        if not (volume.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous()):
+            raise RuntimeError(f"ctclip_b200: the volume must be a contiguous fp32 CUDA tensor (there is no CPU path); "
+                               f"got device={volume.device}, dtype={volume.dtype}, contiguous={volume.is_contiguous()}")
+        if volume.dim() != 5 or volume.shape[1] != 1:
+            raise ValueError(f"ctclip_b200: expected a volume of shape [B, 1, D, H, W], got {tuple(volume.shape)}")
         Bv, _, D, Hv, Wv = volume.shape
         B = batch or Bv
-        assert Bv in (1, B)
-        assert Hv == cfg.image_size and Wv == cfg.image_size
+        if Bv not in (1, B):
+            raise ValueError(f"ctclip_b200: {Bv} volumes for a batch of {B} rows (must be 1 or {B})")
+        if Hv != cfg.image_size or Wv != cfg.image_size or D % cfg.temporal_patch_size or D == 0:
+            raise ValueError(f"ctclip_b200: volume {D}x{Hv}x{Wv} does not tile into {cfg.temporal_patch_size}x"
+                             f"{cfg.patch_size}x{cfg.patch_size} patches of a {cfg.image_size}-pixel model")
         T, H = D // cfg.temporal_patch_size, cfg.hw
         R, C, P = B * T * H * H, cfg.dim, cfg.patch_dim
         bf = torch.bfloat16

@@ -184,6 +184,8 @@ class CTViT(nn.Module):
         if self._standalone_engine is None:
             sd = {"visual_transformer." + k: v for k, v in self.state_dict().items()}
             dev = image.device
+            if dev.type != "cuda":
+                raise RuntimeError(f"ctclip_b200: CTViT runs on sm_100a CUDA devices only (no CPU path); got {dev}")
             sd["to_text_latent.weight"] = torch.zeros(1, 1, device=dev)
             sd["to_visual_latent.weight"] = torch.zeros(1, self.patch_height * self.patch_width * self.dim, device=dev)
             sd["temperature"] = torch.zeros((), device=dev)
@@ -256,7 +258,9 @@ class CTCLIP(nn.Module):
     def engine(self, device=None) -> Engine:
         """Kernel-ready weights are packed on first use (and re-packed after load_state_dict)."""
         if self._engine is None:
-            dev = device or torch.device("cuda", torch.cuda.current_device())
+            dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            if dev.type != "cuda":
+                raise RuntimeError(f"ctclip_b200: CTCLIP runs on sm_100a CUDA devices only (no CPU path); got {dev}")
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith("text_transformer.")}
             cfg = self.visual_transformer.config(self.dim_text, self.dim_latent)
             self._engine = Engine(Plan(sd, cfg, dev))

@@ -116,3 +116,38 @@ def test_module_forward_backward_does_not_leak():
     sim[:, 0].sum().backward(retain_graph=True)
     with pytest.raises(RuntimeError, match="released"):
         sim[:, 0].sum().backward()
+
+
+def test_bad_inputs_fail_loudly():
+    """No CPU path and no silent reshaping: CPU tensors, wrong ranks and volumes that do not tile into patches are
+    rejected with an exception before any kernel is launched."""
+    from models.ctclip import CTCLIP
+    from utils.ctvit import CTViT
+    cfg = O.TINY
+    vit = CTViT(dim=cfg.dim, codebook_size=cfg.codebook_size, image_size=cfg.image_size, patch_size=cfg.patch_size,
+                temporal_patch_size=cfg.temporal_patch_size, spatial_depth=cfg.spatial_depth,
+                temporal_depth=cfg.temporal_depth, dim_head=cfg.dim_head, heads=cfg.heads)
+    H = cfg.image_size // cfg.patch_size
+    clip = CTCLIP(text_encoder=torch.nn.Identity(), image_encoder=vit, dim_text=cfg.dim_text,
+                  dim_image=H * H * cfg.dim, dim_latent=cfg.dim_latent)
+    vol = O.synthetic_volume(cfg, 0)
+    text = O.synthetic_text_embeds(cfg, 7)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        clip(None, vol, text)                                   # model and volume on the CPU
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vit(vol)
+    clip = clip.cuda()
+    eng = clip.engine()
+    tl = eng.text_latents(text.cuda())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        eng.forward(vol, tl)                                    # CPU volume into a CUDA engine
+    with pytest.raises(ValueError, match="shape"):
+        eng.forward(vol.cuda()[0], tl)                          # missing batch axis
+    with pytest.raises(ValueError, match="tile"):
+        eng.forward(vol.cuda()[:, :, :-1].contiguous(), tl)     # depth not a multiple of the temporal patch
+    with pytest.raises(ValueError, match="tile"):
+        eng.forward(vol.cuda()[..., :-4].contiguous(), tl)      # wrong in-plane size
+    with pytest.raises(ValueError, match="volumes for a batch"):
+        eng.forward(torch.cat([vol, vol]).cuda(), tl, batch=3)
+    sim = clip(None, vol.cuda(), text.cuda())[0]                # and the good call still works
+    assert sim.shape == (1, 1) and torch.isfinite(sim).all()
