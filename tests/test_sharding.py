@@ -105,3 +105,38 @@ def test_world2_gloo_combine(parity):
         assert inc == [1] * kept + [0] * (total - kept)
         assert scores[:kept] == [i * 0.5 + 1.0 for i in range(kept)] and all(v == 0 for v in scores[kept:])
         assert part == float(sum(range(50)))
+
+
+def _bcast_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+    A = _attr()
+    acc = SimpleNamespace(is_main_process=rank == 0, process_index=rank, num_processes=world, device=torch.device("cpu"))
+    vis = A.Visualizations(torch.nn.Identity(), acc, None, None, 1, "/tmp/unused", "", None)
+    sample = None
+    if rank == 0:
+        g = torch.Generator().manual_seed(3)
+        sample = (torch.randn(1, 4, 6, 6, generator=g), "report text", torch.arange(18) % 2, "scan7", "scan7.nii.gz")
+    out = vis._broadcast_sample(sample)
+    q.put((rank, out[0].shape, float(out[0].double().sum()), out[1], out[2].tolist(), out[3], out[4]))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_sample_broadcast():
+    """Visualizations._broadcast_sample (visualizations.py:296-318): rank 0 loads the sample, every rank receives the
+    tensors with a leading batch axis and the strings wrapped in lists, exactly as a DataLoader batch looks."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    assert res[0][1:] == res[1][1:]
+    _, shape, _, text, labels, name, path = res[0]
+    assert tuple(shape) == (1, 1, 4, 6, 6) and text == ["report text"] and name == ["scan7"] and path == ["scan7.nii.gz"]
+    assert labels == [[i % 2 for i in range(18)]]
