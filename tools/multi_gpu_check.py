@@ -32,7 +32,12 @@ ok &= bool(torch.equal(aux["scores"][:kept], scores[:kept])) and int(aux["includ
 inc = torch.zeros(len(windows), dtype=torch.uint8, device=dev); inc[:kept] = 1
 heat1 = A.occlusion_heatmap(orig, scores * inc, inc, vol.shape[-3:], ps, st)
 ok &= bool(torch.equal(heat, heat1))
-saved = dist.group.WORLD
+# multi-prompt sweep: one exchange carries the scores of all prompts
+tl3 = eng.text_latents(torch.randn(3, 768, generator=torch.Generator().manual_seed(11)).to(dev))
+heats, maux = A.occlusion_sensitivity_multi(eng, vol, tl3, ps, st, batch=4)
+o3, s3 = A.occlusion_scores(eng, vol, tl3, windows, ps, batch=4, all_prompts=True)
+ok &= bool(torch.equal(maux["scores"][:kept], s3[:kept])) and bool(torch.equal(maux["orig"], o3))
+ok &= int(maux["included"].sum()) == kept and len(heats) == 3
 ig1, iaux1 = A.integrated_gradients(eng, vol, tl, steps=6, batch=3, shard_steps=False)
 rel = float((iaux["gsum"] - iaux1["gsum"]).abs().max() / iaux1["gsum"].abs().max())
 ok &= rel < 1e-5 and bool(torch.equal(iaux["scores"], iaux1["scores"]))
