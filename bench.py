@@ -28,7 +28,19 @@ UNIT = "volumes/s"
 BATCH = 8
 FLOP_FWD = 789.6e9          # SURVEY §8d, per volume
 FLOP_BWD = 707.7e9          # input-gradient only (no weight gradients: attribution never needs them)
-NCU_GEMM_TRAFFIC_BYTES = 610.7e6   # measured offline with ncu (see roofline.traffic_source); not re-measured per run
+
+
+def ncu_gemm_traffic():
+    """roofline.traffic comes from a committed ncu capture, not from a constant in this file: profiles/gemm_traffic.json
+    holds, per GEMM shape of the step, dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch and
+    the commit the capture was taken at (tools/ncu_traffic.py writes it from the raw ncu CSV).  None when absent."""
+    f = ROOT / "profiles" / "gemm_traffic.json"
+    if not f.exists():
+        return None, "no committed ncu capture (profiles/gemm_traffic.json absent)"
+    d = json.loads(f.read_text())
+    return d["mean_bytes_per_launch"], (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, launch-weighted mean over "
+                                        f"the GEMM launches of one step, ncu --set full capture {d['source']} at commit "
+                                        f"{d['commit']}")
 
 
 def load_peaks():
@@ -118,6 +130,179 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
+def pin_to_gpu_numa_node(local: int):
+    """Run this rank (and first-touch its pinned host buffers) on the NUMA node its GPU hangs off: at 8 ranks the e2e
+    step feeds 14 GB per step from host memory and cross-socket traffic halved the per-rank H2D rate.
+    Returns a short description for the JSON line; any failure leaves the affinity untouched."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return "numa_node unknown (-1)"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa node {node}: no allowed cpus"
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception as e:           # noqa: BLE001 - best effort
+        return f"not pinned ({type(e).__name__})"
+
+
+# ------------------------------------------------------------------------------------------ same-box GPU comparator
+def gpu_reference_baseline(dev, steps: int = 3, windows: int = 8):
+    """The reference's REAL GPU path on this box (BASELINE.md §3 "second comparator", SURVEY §2b: "the bar is the
+    PyTorch/cuBLAS path on the same B200"): the oracle = the reference's arithmetic in plain PyTorch, run on the B200
+    under torch.autocast(float16) as the reference runs under Accelerate (CTClipInference.py:56-63).
+      (i)  fwd + input-gradient bwd volumes/s at the largest batch of {8, 4, 2, 1} that fits;
+      (ii) seconds per occlusion window exactly as visualizations.py:376-392 runs the sweep
+           (clone + fill + full forward under no_grad + .item()).
+    Test infrastructure used as the measured COMPARATOR only (like cpu_baseline); never on the product path."""
+    import torch
+    from oracle import ctclip_oracle as O
+    cfg = O.FULL
+    sd = O.to_device(O.init_state_dict(cfg, 42), dev)
+    txt = O.synthetic_text_embeds(cfg, 7).to(dev)
+    out = {"impl": "oracle (reference arithmetic, plain PyTorch/cuBLAS/cuDNN) under torch.autocast(float16) on this B200"}
+
+    def fwd_bwd(x):
+        with torch.autocast("cuda", dtype=torch.float16):
+            sim = O.ctclip_forward(x, txt.expand(x.shape[0], -1), sd, cfg)[0]
+        torch.autograd.grad(sim.diagonal().sum(), x)
+
+    for b in (8, 4, 2, 1):
+        try:
+            x = torch.cat([O.synthetic_volume(cfg, i) for i in range(b)]).to(dev).requires_grad_()
+            fwd_bwd(x)                                               # warm-up (cuDNN / cuBLAS heuristics, allocator)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fwd_bwd(x)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out["fwd_bwd"] = {"value": b / (ms / 1e3), "unit": UNIT, "batch": b, "ms_per_step": ms, "steps": steps}
+            break
+        except torch.OutOfMemoryError:
+            x = None
+            torch.cuda.empty_cache()
+    x = None
+    torch.cuda.empty_cache()
+    vol = O.synthetic_volume(cfg, 0).to(dev)
+    wins = O.occlusion_windows((240, 480, 480))[6000:6000 + windows]
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        float(O.ctclip_forward(vol, txt, sd, cfg)[0][0, 0])           # warm-up + the sweep's baseline forward
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for (d, h, w) in wins:
+            occ = vol.clone()
+            occ[:, :, d:d + 20, h:h + 40, w:w + 40] = -1
+            float(O.ctclip_forward(occ, txt, sd, cfg)[0][0, 0])      # .item(): visualizations.py:388
+        per = (time.perf_counter() - t0) / len(wins)
+    out["occlusion"] = {"seconds_per_window": per, "windows_timed": len(wins),
+                        "extrapolated_sweep_s": per * 12168, "loop": "visualizations.py:376-392"}
+    torch.cuda.empty_cache()
+    return out
+
+
+def cublas_gemm_comparison(shapes, dev):
+    """cuBLAS (torch.matmul, bf16 operands, fp32 accumulate) on exactly the GEMM shapes of one step, next to
+    gemm_tcgen05_kernel.  shapes: list of (M, N, K, our_ms).  Output fp32 vs bf16 and the fused epilogues are OUR
+    side's extra work; cuBLAS runs the bare bf16 -> bf16 GEMM, i.e. this flatters the library."""
+    import torch
+    from collections import OrderedDict
+    agg = OrderedDict()
+    for (M, N, K, ms) in shapes:
+        a = agg.setdefault((M, N, K), [0, 0.0])
+        a[0] += 1
+        a[1] += ms
+    rows, tot_f, tot_ours, tot_lib = [], 0.0, 0.0, 0.0
+    for (M, N, K), (cnt, ours_ms) in agg.items():
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            torch.matmul(a, w.t())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            torch.matmul(a, w.t())
+        e1.record()
+        torch.cuda.synchronize()
+        lib_ms = e0.elapsed_time(e1) / 10
+        fl = 2.0 * M * N * K
+        rows.append({"M": M, "N": N, "K": K, "launches_per_step": cnt, "ours_ms": ours_ms / cnt, "cublas_ms": lib_ms,
+                     "ours_tflops": fl / (ours_ms / cnt) / 1e9, "cublas_tflops": fl / lib_ms / 1e9})
+        tot_f += fl * cnt
+        tot_ours += ours_ms
+        tot_lib += lib_ms * cnt
+        del a, w
+    return {"per_shape": rows, "ours_tflops": tot_f / tot_ours / 1e9, "cublas_tflops": tot_f / tot_lib / 1e9,
+            "note": "padded (executed) shapes; cuBLAS timed back to back (warm L2), ours inside the step"}
+
+
+def cpu_attribution_baselines():
+    """BASELINE.md §3 configs on the box's host cores (oracle, fp32, all threads): C1 rollout + Grad-CAM of one volume
+    timed in full; C3 integrated gradients at alpha in {0, 0.5, 1}, extrapolated x 50/3; C4 occlusion: 8 windows + the
+    baseline forward, extrapolated linearly to 12 167 windows."""
+    import torch
+    from oracle import ctclip_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.FULL
+    sd = O.init_state_dict(cfg, 42)
+    txt = O.synthetic_text_embeds(cfg, 7)
+    vol = O.synthetic_volume(cfg, 0)
+    out = {"cores": os.cpu_count(), "kind": "port"}
+    t0 = time.perf_counter()
+    x = vol.clone().requires_grad_()
+    cap = {}
+    sim = O.ctclip_forward(x, txt, sd, cfg, cap)[0]
+    O.grad_cam_maps(sim[0, 0], cap)
+    O.rollout_maps([a.detach() for a in cap["spatial_attention_weights"]],
+                   [a.detach() for a in cap["temporal_attention_weights"]])
+    out["C1_rollout_gradcam_s"] = time.perf_counter() - t0
+    del cap, sim, x
+    t0 = time.perf_counter()
+    for alpha in (0.0, 0.5, 1.0):
+        xa = (1 + alpha * (vol - 1)).requires_grad_()
+        torch.autograd.grad(O.ctclip_forward(xa, txt, sd, cfg)[0][0, 0], xa)
+    t = time.perf_counter() - t0
+    out["C3_ig_3_alpha_s"] = t
+    out["C3_ig_50_steps_extrapolated_s"] = t * 50 / 3
+    wins = O.occlusion_windows((240, 480, 480))[6000:6008]
+    t0 = time.perf_counter()
+    O.occlusion_scores(vol, txt, sd, cfg, wins, (20, 40, 40))
+    t = time.perf_counter() - t0
+    out["C4_occlusion_8_windows_plus_baseline_s"] = t
+    out["C4_occlusion_12167_windows_extrapolated_s"] = t / 9 * 12168
+    out["attributed_volume_extrapolated_s"] = out["C4_occlusion_12167_windows_extrapolated_s"] + out["C3_ig_50_steps_extrapolated_s"]
+    return out
+
+
+def run_reference_gpu(args):
+    """`--impl reference-gpu`: the same-box PyTorch-GPU comparator alone, as its own JSON line (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    g = gpu_reference_baseline(dev, steps=max(args.steps, 1))
+    fb = g["fwd_bwd"]
+    emit({"impl": "reference-gpu", "metric": METRIC, "value": fb["value"], "unit": UNIT, "n_gpus": 1, "steps": fb["steps"],
+          "warmup": 1, "ms_per_step": fb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f16-autocast", "data": "synthetic",
+          "config": {"workload": "ctvit_fwd_bwd_b8_480x480x240", "volumes_per_step": fb["batch"]}, "gpu_baseline": g})
+
+
 # ------------------------------------------------------------------------------------------ attribution sub-metric
 def occlusion_flops(T=24, HW=576, n_layers=4, nt=2):
     """(dense-equivalent, executed) FLOPs of one reference-sized occlusion sweep (12 167 windows + baseline),
@@ -157,7 +342,7 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
         e[2].record()
         # both maps on the host (pinned staging buffers) - on rank 0, the process that saves them
         # (visualizations.py:411-424, 903-906); the other ranks only finish their device work
-        out = (A.to_host(heat, 0), A.to_host(ig, 1)) if rank == 0 else (heat, ig)
+        out = (A.to_host(heat, 0), A.to_host(ig, 1)) if rank == 0 else (heat, heat)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         return (wall, e[0].elapsed_time(e[1]) / 1e3, e[1].elapsed_time(e[2]) / 1e3, int(aux["included"].sum()), out,
@@ -175,6 +360,11 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
     A.occlusion_scores(eng, host_vol.to(dev), tl, A.occlusion_windows(tuple(host_vol.shape[-3:]))[:32], (20, 40, 40),
                        skip_noop=False)
     if world > 1:
+        # the first large NCCL collective sets up channels / buffers (tens of ms): a service pays that once, so one
+        # untimed reduce of the IG partial-sum size runs before the timed pass
+        warm = torch.zeros(tuple(host_vol.shape[-3:]), device=dev)
+        dist.reduce(warm, dst=0)
+        del warm
         dist.barrier()
     torch.cuda.synchronize()
 
@@ -187,16 +377,16 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
         t0 = time.perf_counter()
         sp, tp = A.attention_rollout_maps(eng, vol, tl)
         for m in (sp, tp):
-            A.to_host(A.upsample(m, shape), 0)        # pinned staging, consumed map by map as _save does
+            A.to_host(A.upsample(m, shape), 0, view=True)   # pinned staging, consumed map by map as _save does
         torch.cuda.synchronize(); out["attention_rollout_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         cams = A.grad_cam(eng, vol, tl)
         for k in ("spatial_ff", "temporal_ff", "spatial", "temporal", "combined", "vq"):
-            A.to_host(A.upsample(cams[k], shape), 0)
+            A.to_host(A.upsample(cams[k], shape), 0, view=True)
         torch.cuda.synchronize(); out["grad_cam_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         rs, rt = A.raw_attention_maps(eng, vol, tl)
-        A.to_host(rs, 2); A.to_host(rt, 3)
+        A.to_host(rs, 2, view=True); A.to_host(rt, 3, view=True)
         torch.cuda.synchronize(); out["raw_attention_s"] = time.perf_counter() - t0
         # zero-shot scoring of the 18 pathologies (CTClipInference.py:147-190): H2D of the volume, ONE image forward
         # against the 36 cached prompt latents, pair softmax, D2H of the 18 probabilities
@@ -211,7 +401,6 @@ def run_attribution(eng, host_vol, tl, dev, world, dist):
     # headline: EVERY window of the sweep is evaluated.  Second pass: windows that lie entirely in -1 air / padding
     # (no-ops, score == baseline bit for bit) are detected on the device and skipped - reported separately.
     wall, occ_s, ig_s, n_win, maps, _ = once(False)
-    maps = tuple(m.clone() for m in maps)            # the pinned staging buffers are re-used by the next pass
     wall2, occ2_s, _, _, maps2, stats = once(True)
     same = bool(torch.equal(maps[0], maps2[0]))
     t = torch.tensor([wall, occ_s, ig_s, wall2, occ2_s], device=dev)
@@ -247,6 +436,7 @@ def run_product(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -409,30 +599,43 @@ def run_product(args):
         s.record()
         r = orig_gemm(a, w, out, epi, bias=bias, resid=resid, aux=aux)
         e.record()
-        events.append((2.0 * a.shape[0] * algo(a.shape[1]) * algo(w.shape[0]), s, e))
+        events.append((2.0 * a.shape[0] * algo(a.shape[1]) * algo(w.shape[0]), s, e, (a.shape[0], w.shape[0], a.shape[1])))
         return r
     eng.gemm = timed_gemm
     step_device()
     torch.cuda.synchronize()
     eng.gemm = orig_gemm
-    gemm_flops = sum(f for f, _, _ in events)
-    gemm_ms = sum(s.elapsed_time(e) for _, s, e in events)
+    gemm_flops = sum(ev[0] for ev in events)
+    gemm_ms = sum(ev[1].elapsed_time(ev[2]) for ev in events)
+    gemm_shapes = [(*ev[3], ev[1].elapsed_time(ev[2])) for ev in events]
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12
+    traffic, traffic_src = ncu_gemm_traffic()
     roofline = {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf"],
-                "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": NCU_GEMM_TRAFFIC_BYTES,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the six distinct "
-                                  "forward GEMM shapes of one layer in the ncu --set full capture "
-                                  "profiles/r01_launches_step_b8_v2.md (equals their algorithmic bytes)",
+                "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                 "launches_per_step": len(events), "gemm_ms_per_step": gemm_ms,
                 "share_of_step": gemm_ms / ms_step}
 
     # ---- the attribution sub-metric (occlusion sweep + IG-50 of one volume, sharded over the ranks)
     attribution = None
+    del bufs, vol, grad, ctx, graph
+    torch.cuda.empty_cache()
     if not args.no_attribution:
-        del bufs, vol, grad, ctx, graph
-        torch.cuda.empty_cache()
         attribution = run_attribution(eng, host[:1], tl, dev, world, dist)
+
+    # ---- N > 1: the sharded path must reproduce the single-rank result (untimed; every rank takes part)
+    parity = None
+    if world > 1 and not args.no_parity:
+        from ctclip_b200.selfcheck import sharding_parity
+        parity = sharding_parity(eng, host[:1].to(dev), tl)
+        torch.cuda.empty_cache()
+
+    # ---- same-box comparators (rank 0, N = 1): cuBLAS on the step's GEMM shapes, the reference's PyTorch GPU path
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        gpu_base = gpu_reference_baseline(dev)
+        gpu_base["cublas_gemm"] = cublas_gemm_comparison(gemm_shapes, dev)
 
     if rank != 0:
         if world > 1:
@@ -444,6 +647,8 @@ def run_product(args):
         secs = cpu_oracle_fwd_bwd(1)
         cpu = {"value": 1.0 / secs, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": "1 volume fwd+input-grad bwd (1/8 of one step), oracle fp32, all host threads"}
+        if attribution is not None:
+            attribution["cpu_baseline"] = cpu_attribution_baselines()
     step_flops = (FLOP_FWD + FLOP_BWD) * BATCH
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -459,7 +664,7 @@ def run_product(args):
                 "d2h_bytes_per_step": int(res.numel() * 4) * world,
                 "api": "CTCLIP.forward + sim.backward(); H2D of step i+1 and the host read of step i-1's result overlap the "
                        "compute of step i (every result is read inside the timed region)",
-                "h2d_gbps_this_box": h2d_gbps,
+                "h2d_gbps_this_box": h2d_gbps, "steps": e2e_steps, "host_affinity": numa,
                 "bound": "PCIe: max(compute, H2D of the 1.77 GB fp32 batch per rank); compute alone is ms_per_step"},
         "gpu_launches": int(launches),
         "roofline": roofline,
@@ -467,6 +672,10 @@ def run_product(args):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
+    if gpu_base is not None:
+        out["gpu_baseline"] = gpu_base
+    if parity is not None:
+        out["parity"] = parity
     if attribution is not None:
         out["attribution"] = attribution
     emit(out)
@@ -491,6 +700,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-attribution", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its
     # version banner there when the box sets NCCL_DEBUG=VERSION) are sent to stderr for the duration of the run.
@@ -500,6 +711,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_product(args)
 

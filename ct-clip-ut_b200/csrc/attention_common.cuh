@@ -234,7 +234,8 @@ inline int fill_params(AttnParams& p, int B, int T, int H, int W, int heads, int
 
 template <void (*kern)(const AttnParams)>
 static int launch_attn(const AttnParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;   // one static per kernel (the kernel is a non-type template argument)
+    static size_t configured_dev[kMaxDevices] = {};   
+    size_t& configured = configured_dev[current_device()];   // one static per kernel (the kernel is a non-type template argument)
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // without this the driver sizes the shared-memory carve-out for ONE block (ncu: occupancy_limit_shared_mem = 1)

@@ -614,7 +614,9 @@ int run_tc_bwd_dq(const AttnParams& p, cudaStream_t st) {
     const size_t nb = (size_t)(2 * p.H - 1) * (2 * p.W - 1);
     const size_t smem = 1024 + 4 * (size_t)TC_M * 64 + 3 * (size_t)p.n_pad * 64 + ((nb + 1) & ~(size_t)1) * 8 +
                         (((size_t)p.n_pad / 8 + 3) & ~(size_t)3) * 4 + 256 + 2 * TC_M * 4 + 128;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};
+    
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_dq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -630,7 +632,9 @@ int run_tc_fwd(const AttnParams& p, float score_bound, cudaStream_t st) {
     const size_t nb = (size_t)(2 * p.H - 1) * (2 * p.W - 1);
     const size_t smem = 1024 + 2 * (size_t)TC_M * 64 + (size_t)p.n_pad * 128 + ((nb + 1) & ~(size_t)1) * 8 +
                         (((size_t)p.n_pad / 8 + 3) & ~(size_t)3) * 4 + 256 + TC_M * 4 + 64;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};
+    
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,

@@ -11,39 +11,131 @@ namespace ctc {
 // ---------------------------------------------------------------------------------------------
 // spatial "rollout": the reference calls attention_rollout([P_slice]) with ONE matrix, so
 //   A = mean_h P;  A /= (rowsum + 1e-8);  A += I;  A /= rowsum;  result = A @ I;  out = colsum(A)
-// One CTA per (slice, 8-row group): each warp owns a row, accumulates its column contributions
-// into shared memory, then one atomicAdd per column per CTA.
+// One CTA per slice.  Pass 1: a warp per row computes the two row normalisers; pass 2: a thread per
+// column adds the rows in order.  No atomics: the result is bit-reproducible.  `probs` is
+// [n_slices, heads, n, n]; with the head-fused matrix of ctc_attention_fused_probs, heads = 1.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 rollout_spatial_kernel(const float* __restrict__ probs, int heads, int n, float* __restrict__ out) {
-    extern __shared__ float col[];  // [n]
+    extern __shared__ float rn[];   // [2n]: 1/d1, 1/r2 per row
     const int s = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) col[j] = 0.f;
-    __syncthreads();
     const float invh = 1.f / heads;
-    for (int i = blockIdx.y * nw + warp; i < n; i += gridDim.y * nw) {
-        // pass 1: row sum of the head mean
+    const float* P = probs + (long long)s * heads * n * n;
+    for (int i = warp; i < n; i += nw) {
         float rs = 0.f;
         for (int j = lane; j < n; j += 32) {
             float a = 0.f;
-            for (int h = 0; h < heads; ++h) a += probs[(((long long)s * heads + h) * n + i) * n + j];
+            for (int h = 0; h < heads; ++h) a += P[((long long)h * n + i) * n + j];
             rs += a * invh;
         }
         rs = warp_sum(rs);
-        const float d1 = rs + 1e-8f;
-        // second normaliser: sum_j (A_ij / d1) + 1
-        const float r2 = rs / d1 + 1.f;
-        for (int j = lane; j < n; j += 32) {
-            float a = 0.f;
-            for (int h = 0; h < heads; ++h) a += probs[(((long long)s * heads + h) * n + i) * n + j];
-            float v = a * invh / d1;
-            if (j == i) v += 1.f;
-            atomicAdd(&col[j], v / r2);
+        if (lane == 0) {
+            const float d1 = rs + 1e-8f;
+            rn[2 * i] = d1;
+            rn[2 * i + 1] = rs / d1 + 1.f;          // second normaliser: sum_j (A_ij / d1) + 1
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += blockDim.x) atomicAdd(&out[(long long)s * n + j], col[j]);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) {
+            float a = 0.f;
+            for (int h = 0; h < heads; ++h) a += P[((long long)h * n + i) * n + j];
+            float v = a * invh / rn[2 * i];
+            if (j == i) v += 1.f;
+            acc += v / rn[2 * i + 1];
+        }
+        out[(long long)s * n + j] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic Visualizations.attention_rollout (visualizations.py:707-743), one layer: head fusion
+// (mean / max), optional discard of the lowest weights of each row (keep the k_keep largest:
+// `flat.topk(n - num_discard).min()` is the k_keep-th largest value, found exactly by rank counting),
+// A /= (rowsum + 1e-8), and with the residual A += I, A /= rowsum.  One CTA per row, n <= 1024.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rollout_fuse_kernel(const float* __restrict__ attn, int heads, int n, int fusion_max, int k_keep, int use_residual,
+                    float* __restrict__ out) {
+    extern __shared__ float row[];            // [n] fused row, then [8] reduction scratch
+    float* red = row + n;
+    __shared__ float s_thr;
+    const int i = blockIdx.x;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float a = fusion_max ? -3.0e38f : 0.f;
+        for (int h = 0; h < heads; ++h) {
+            const float v = attn[((long long)h * n + i) * n + j];
+            a = fusion_max ? fmaxf(a, v) : a + v;
+        }
+        row[j] = fusion_max ? a : a / (float)heads;
+    }
+    __syncthreads();
+    if (k_keep < n) {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const float x = row[j];
+            int gt = 0, ge = 0;
+            for (int m = 0; m < n; ++m) { const float y = row[m]; gt += y > x; ge += y >= x; }
+            if (gt < k_keep && k_keep <= ge) s_thr = x;       // every match carries the same value
+        }
+        __syncthreads();
+        const float thr = s_thr;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) if (!(row[j] >= thr)) row[j] = 0.f;
+        __syncthreads();
+    }
+    auto block_sum = [&](float v) {           // fixed-order block reduction
+        v = warp_sum(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        return t;
+    };
+    float part = 0.f;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) part += row[j];
+    const float d1 = block_sum(part) + 1e-8f;
+    part = 0.f;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float v = row[j] / d1;
+        if (use_residual && j == i) v += 1.f;
+        row[j] = v;
+        part += v;
+    }
+    const float r2 = use_residual ? block_sum(part) : 1.f;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) out[(long long)i * n + j] = use_residual ? row[j] / r2 : row[j];
+}
+
+// C = A @ B, fp32 row-major n x n (the `result = attn @ result` chain of the generic rollout); 32 x 32 tiles
+__global__ void __launch_bounds__(1024)
+matmul_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, int n, float* __restrict__ C) {
+    __shared__ float sa[32][33], sb[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.y * 32 + ty, col = blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        sa[ty][tx] = (row < n && k0 + tx < n) ? A[(long long)row * n + k0 + tx] : 0.f;
+        sb[ty][tx] = (k0 + ty < n && col < n) ? B[(long long)(k0 + ty) * n + col] : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc = fmaf(sa[ty][k], sb[k][tx], acc);
+        __syncthreads();
+    }
+    if (row < n && col < n) C[(long long)row * n + col] = acc;
+}
+
+// dst[i] (+)= sum_b src[b, i] * scale, batch rows added in order (the IG running sum, visualizations.py:872,878)
+__global__ void __launch_bounds__(256)
+batch_sum_kernel(const float* __restrict__ src, int B, long long n, float scale, int accumulate, float* __restrict__ dst) {
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+        float4 a = accumulate ? *reinterpret_cast<const float4*>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < B; ++b) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (long long)b * n + i);
+            a.x += v.x * scale; a.y += v.y * scale; a.z += v.z * scale; a.w += v.w * scale;
+        }
+        *reinterpret_cast<float4*>(dst + i) = a;
+    }
 }
 
 // temporal rollout: chain L layers of [T, T] head-mean matrices per token (T <= 32): one warp per token,
@@ -105,16 +197,24 @@ attn_colmean_kernel(const float* __restrict__ probs, int n, float* __restrict__ 
     }
 }
 
-// w[c] += sum_r g[r, c] / R over this CTA's row slab (w must be zeroed by the caller)
+// part[blk, c] = sum_r g[r, c] over this CTA's row slab; colmean_final adds the slabs in order (no atomics)
 __global__ void __launch_bounds__(256)
-colmean_kernel(const float* __restrict__ g, long long R, int C, float invR, float* __restrict__ w) {
+colmean_kernel(const float* __restrict__ g, long long R, int C, float* __restrict__ part) {
     const long long rows_per = (R + gridDim.x - 1) / gridDim.x;
     const long long r0 = blockIdx.x * rows_per, r1 = min(R, r0 + rows_per);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a = 0.f;
         for (long long r = r0; r < r1; ++r) a += g[r * C + c];
-        atomicAdd(&w[c], a * invR);
+        part[(long long)blockIdx.x * C + c] = a;
     }
+}
+__global__ void __launch_bounds__(256)
+colmean_final_kernel(const float* __restrict__ part, int nblk, int C, float invR, float* __restrict__ w) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f;
+    for (int b = 0; b < nblk; ++b) a += part[(long long)b * C + c];
+    w[c] = a * invR;
 }
 
 // cam[r] = relu(sum_c (fa[r,c] - fb[r,c]) * w[c]); warp per row
@@ -248,14 +348,71 @@ normalize_kernel(const float* __restrict__ in, int D, int H, int W, const float*
 }
 
 // 16-bit radix histogram of the fp32 bit patterns (non-negative values: bit order == numeric order).
-// Counts (bits >> shift) & 0xffff of the elements whose bits above (shift+16) equal `prefix`.
+// Counts (bits >> shift) & 0xffff of the elements whose bits above (shift+16) equal the prefix (shift == 0 only;
+// the prefix comes from `prefix_dev` when given, so that a two-pass selection needs no host round trip).
+// Exact zeros — half of a relu'd integrated-gradients map — are counted per warp with one atomic.
 __global__ void __launch_bounds__(256)
-hist16_kernel(const float* __restrict__ x, long long n, int shift, unsigned int prefix, unsigned int* __restrict__ hist) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned int b = __float_as_uint(x[i]);
-        if (shift == 0 && (b >> 16) != prefix) continue;
-        atomicAdd(&hist[(b >> shift) & 0xffffu], 1u);
+hist16_kernel(const float* __restrict__ x, long long n, int shift, unsigned int prefix,
+              const unsigned int* __restrict__ prefix_dev, unsigned int* __restrict__ hist) {
+    if (prefix_dev) prefix = *prefix_dev;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long base = i0 - threadIdx.x % 32; base < n; base += stride) {     // warp-uniform trip count
+        const long long i = base + threadIdx.x % 32;
+        const bool in = i < n;
+        const unsigned int b = in ? __float_as_uint(x[i]) : 0xffffffffu;
+        const bool take = in && !(shift == 0 && (b >> 16) != prefix);
+        const bool zero = take && ((b >> shift) & 0xffffu) == 0u;
+        const unsigned int zmask = __ballot_sync(0xffffffffu, zero);
+        if (zmask && (threadIdx.x % 32) == (unsigned)(__ffs(zmask) - 1)) atomicAdd(&hist[0], (unsigned)__popc(zmask));
+        if (take && !zero) atomicAdd(&hist[(b >> shift) & 0xffffu], 1u);
     }
+}
+
+// Bucket of a 65536-bin histogram that holds the element of 0-based rank k (one CTA of 1024 threads, 64 bins each).
+//   pass 0: k = k_imm;            writes sel[0] = bucket, rank_left = k - (elements before the bucket)
+//   pass 1: k = rank_left (read); writes the selected VALUE bits (sel[0] << 16 | bucket) to out
+struct KthState { unsigned long long rank_left; unsigned int hi; unsigned int pad; };
+__global__ void __launch_bounds__(1024)
+hist_select_kernel(const unsigned int* __restrict__ hist, long long k_imm, int pass, KthState* __restrict__ st,
+                   float* __restrict__ out) {
+    __shared__ unsigned long long wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long k = pass == 0 ? (unsigned long long)k_imm : st->rank_left;
+    unsigned long long local = 0;
+    for (int b = 0; b < 64; ++b) local += hist[tid * 64 + b];
+    unsigned long long inc = local;                                   // inclusive scan inside the warp
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned long long before = inc - local;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    if (k >= before && k < before + local) {                          // exactly one thread
+        unsigned long long c = before;
+        for (int b = 0; b < 64; ++b) {
+            const unsigned int h = hist[tid * 64 + b];
+            if (k < c + h) {
+                const unsigned int bucket = tid * 64 + b;
+                if (pass == 0) { st->hi = bucket; st->rank_left = k - c; }
+                else *out = __uint_as_float((st->hi << 16) | bucket);
+                break;
+            }
+            c += h;
+        }
+    }
+}
+
+// np.quantile's linear interpolation between the two order statistics, in float32 like NumPy 2.x does for an fp32 array
+__global__ void quantile_lerp_kernel(const float* __restrict__ a_dev, const float* __restrict__ b_dev, float gamma,
+                                     float* __restrict__ out) {
+    const float a = *a_dev, b = *b_dev;
+    const float d = b - a;
+    float r = a + d * gamma;
+    if (gamma >= 0.5f) r = b - d * (1.f - gamma);
+    *out = r;
 }
 
 // integrated-gradients finalisation, second half (visualizations.py:882-901):
@@ -272,6 +429,26 @@ ig_finalize_kernel(const float* __restrict__ ig, int D, int H, int W, float mn, 
     const float n1 = (ig[((long long)z * H + y) * W + x] - mn) / (mx + 1e-8f);
     const float n2 = (n1 >= q) ? n1 : 0.f;
     out[idx] = (n2 > 0.f ? powf(n2, 0.05f) : 0.f) * inv_m3;
+}
+
+// same, with min / max / quantile read from device memory (no host round trip between the IG stages).  The
+// final scale follows the reference's float32 pipeline literally: n1max = (max-min)/(max+1e-8),
+// m3 = n1max >= q ? n1max ** 0.05 : 0, out = n3 / (m3 + 1e-8).
+__global__ void __launch_bounds__(256)
+ig_finalize_dev_kernel(const float* __restrict__ ig, int D, int H, int W, const float* __restrict__ mm,
+                       const float* __restrict__ q_dev, int rot, float* __restrict__ out) {
+    const int OY = rot ? W : H, OX = rot ? H : W;
+    const long long total = (long long)D * OY * OX;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const float mn = mm[0], mx = mm[1], q = *q_dev;
+    const float n1max = (mx - mn) / (mx + 1e-8f);
+    const float m3 = (n1max >= q && n1max > 0.f) ? powf(n1max, 0.05f) : 0.f;
+    const int ox = (int)(idx % OX), oy = (int)((idx / OX) % OY), z = (int)(idx / ((long long)OX * OY));
+    const int y = rot ? (H - 1 - ox) : oy, x = rot ? oy : ox;
+    const float n1 = (ig[((long long)z * H + y) * W + x] - mn) / (mx + 1e-8f);
+    const float n2 = (n1 >= q) ? n1 : 0.f;
+    out[idx] = (n2 > 0.f ? powf(n2, 0.05f) : 0.f) / (m3 + 1e-8f);
 }
 
 // occlusion heat map (visualizations.py:366-367, 390-392, 411-413): windows form a regular grid
@@ -372,7 +549,40 @@ extern "C" int ctc_normalize(const float* in, int D, int H, int W, const float* 
 extern "C" int ctc_hist16(const float* x, int64_t n, int shift, unsigned int prefix, unsigned int* hist, void* stream) {
     CTC_REQUIRE(shift == 0 || shift == 16, "hist16: shift must be 0 or 16");
     CTC_CHECK_CUDA(cudaMemsetAsync(hist, 0, 65536 * sizeof(unsigned int), (cudaStream_t)stream));
-    hist16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(x, n, shift, prefix, hist);
+    hist16_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(x, n, shift, prefix, nullptr, hist);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_kth_value_ws_bytes(void) { return 65536 * 4 + (int)sizeof(KthState); }
+
+extern "C" int ctc_kth_value(const float* x, int64_t n, int64_t k, void* ws, float* out_dev, void* stream) {
+    CTC_REQUIRE(n > 0 && k >= 0 && k < n, "kth_value: k=%lld outside [0, %lld)", (long long)k, (long long)n);
+    CTC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "kth_value: workspace must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(ws);
+    KthState* state = reinterpret_cast<KthState*>(hist + 65536);
+    for (int pass = 0; pass < 2; ++pass) {
+        CTC_CHECK_CUDA(cudaMemsetAsync(hist, 0, 65536 * sizeof(unsigned int), st));
+        hist16_kernel<<<148 * 8, 256, 0, st>>>(x, n, pass == 0 ? 16 : 0, 0u, pass == 0 ? nullptr : &state->hi, hist);
+        CTC_LAUNCH_CHECK();
+        hist_select_kernel<<<1, 1024, 0, st>>>(hist, k, pass, state, out_dev);
+        CTC_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int ctc_quantile_lerp(const float* a_dev, const float* b_dev, float gamma, float* out_dev, void* stream) {
+    quantile_lerp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a_dev, b_dev, gamma, out_dev);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_ig_finalize_dev(const float* ig, int D, int H, int W, const float* mm_dev, const float* q_dev,
+                                   int rot90, float* out, void* stream) {
+    const long long total = (long long)D * H * W;
+    ig_finalize_dev_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ig, D, H, W, mm_dev, q_dev,
+                                                                                             rot90, out);
     CTC_LAUNCH_CHECK();
     return 0;
 }
@@ -396,9 +606,36 @@ extern "C" int ctc_occlusion_heatmap(const float* imp, const unsigned char* inc,
 }
 
 extern "C" int ctc_rollout_spatial(const float* probs, int n_slices, int heads, int n, float* out, void* stream) {
-    CTC_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)n_slices * n * sizeof(float), (cudaStream_t)stream));
-    dim3 grid(n_slices, 8);
-    rollout_spatial_kernel<<<grid, 256, n * sizeof(float), (cudaStream_t)stream>>>(probs, heads, n, out);
+    CTC_REQUIRE(n > 0 && (size_t)n * 8 <= 48 * 1024, "rollout_spatial: n=%d outside (0, 6144]", n);
+    rollout_spatial_kernel<<<n_slices, 512, 2 * n * sizeof(float), (cudaStream_t)stream>>>(probs, heads, n, out);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_rollout_fuse(const float* attn, int heads, int n, int fusion, int k_keep, int use_residual,
+                                float* out, void* stream) {
+    CTC_REQUIRE(heads > 0 && n > 0 && n <= 4096, "rollout_fuse: heads=%d n=%d", heads, n);
+    CTC_REQUIRE(fusion == 0 || fusion == 1, "rollout_fuse: fusion must be 0 (mean) or 1 (max), got %d", fusion);
+    CTC_REQUIRE(k_keep >= 1 && k_keep <= n, "rollout_fuse: k_keep=%d outside [1, %d]", k_keep, n);
+    rollout_fuse_kernel<<<n, 256, (n + 8) * sizeof(float), (cudaStream_t)stream>>>(attn, heads, n, fusion, k_keep,
+                                                                                  use_residual, out);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_matmul_f32(const float* A, const float* B, int n, float* C, void* stream) {
+    CTC_REQUIRE(n > 0 && C != A && C != B, "matmul_f32: n=%d, output must not alias an input", n);
+    dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 32);
+    matmul_f32_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, B, n, C);
+    CTC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ctc_batch_sum(const float* src, int B, int64_t n, float scale, int accumulate, float* dst, void* stream) {
+    CTC_REQUIRE(B > 0 && n > 0 && n % 4 == 0, "batch_sum: B=%d n=%lld (n must be a multiple of 4)", B, (long long)n);
+    CTC_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
+                "batch_sum: buffers must be 16-byte aligned");
+    batch_sum_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(src, B, n, scale, accumulate, dst);
     CTC_LAUNCH_CHECK();
     return 0;
 }
@@ -417,10 +654,14 @@ extern "C" int ctc_attn_colmean(const float* probs, int n_seq, int heads, int n,
     return 0;
 }
 
-extern "C" int ctc_colmean(const float* g, int R, int C, float* w, void* stream) {
-    CTC_CHECK_CUDA(cudaMemsetAsync(w, 0, (size_t)C * sizeof(float), (cudaStream_t)stream));
+extern "C" int ctc_colmean_ws_floats(int R, int C) { return (R < 592 ? R : 592) * C; }
+
+extern "C" int ctc_colmean(const float* g, int R, int C, float* w, float* ws, void* stream) {
+    CTC_REQUIRE(R > 0 && C > 0 && ws != nullptr, "colmean: R=%d C=%d, workspace of ctc_colmean_ws_floats(R, C) floats required", R, C);
     const int grid = R < 592 ? R : 592;
-    colmean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, R, C, 1.f / (float)R, w);
+    colmean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, R, C, ws);
+    CTC_LAUNCH_CHECK();
+    colmean_final_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, grid, C, 1.f / (float)R, w);
     CTC_LAUNCH_CHECK();
     return 0;
 }

@@ -32,6 +32,14 @@ void set_last_error(const char* fmt, ...);
         }                                                                               \
     } while (0)
 void count_launch();
+// The dynamic-shared-memory attribute of a kernel and the SM count are per DEVICE: every "configured once" flag is
+// keyed by the current device so that one process can drive engines on several GPUs.
+static constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
 #define CTC_LAUNCH_CHECK()                    \
     do {                                      \
         ::ctc::count_launch();                \

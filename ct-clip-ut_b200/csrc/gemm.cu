@@ -566,21 +566,21 @@ static int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long rows, lon
     return 0;
 }
 
-static int g_num_sms = 0;
+static int g_num_sms[kMaxDevices] = {};
 int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    const int dev = current_device();
+    if (!g_num_sms[dev]) {
+        cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms[dev] <= 0) g_num_sms[dev] = 148;
     }
-    return g_num_sms;
+    return g_num_sms[dev];
 }
 
 template <int BN, int EPI>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
     using S = GemmSmem<BN>;
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool& configured = configured_dev[current_device()];
     if (!configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             S::kTotal));

@@ -346,7 +346,9 @@ extern "C" int ctc_patchify_ln_fwd(const float* volume, int64_t vol_batch_stride
     PatchGeom g;
     if (int e = make_geom(g, vol_batch_stride, B, D, H, W, pt, p, 4)) return e;
     const size_t smem = (size_t)g.G * g.P * 4;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};
+    
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -374,7 +376,9 @@ extern "C" int ctc_patchify_ln_bwd(const float* volume, int64_t vol_batch_stride
     PatchGeom g;
     if (int e = make_geom(g, vol_batch_stride, B, D, H, W, pt, p, 6)) return e;
     const size_t smem = (size_t)g.G * g.P * 6;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};
+    
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
         CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CTC_CHECK_CUDA(cudaFuncSetAttribute(patchify_ln_bwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,

@@ -188,7 +188,8 @@ int peg_tma_launch(const float* x, int B, int T, int H, int W, int C, const floa
     const bool cw24 = (W == 24);
 #define PT_LAUNCH(CWV, BF)                                                                                        \
     do {                                                                                                          \
-        static size_t configured = 0;                                                                             \
+        static size_t configured_dev[kMaxDevices] = {};                                                                             \
+    size_t& configured = configured_dev[current_device()];                                                                             \
         if (smem > configured) {                                                                                  \
             CTC_CHECK_CUDA(cudaFuncSetAttribute(peg_tma_kernel<CWV, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                 (int)smem));                                                      \

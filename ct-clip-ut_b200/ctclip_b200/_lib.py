@@ -35,6 +35,7 @@ SIGNATURES = {
     "ctc_attention_score_bound": [P, P, F, P, I, I, I, P, P],
     "ctc_attention_bwd": [P, L, P, P, L, P, P, P, I, I, I, I, I, P, P, F, P, I, P, L, P, P, L, P, P],
     "ctc_attention_probs": [P, L, P, L, P, I, I, I, I, I, P, P, F, P, I, P, P],
+    "ctc_attention_fused_probs": [P, L, P, L, P, I, I, I, I, I, P, P, F, P, I, I, P, P, P, P],
     "ctc_geglu_fwd": [P, I, I, P, P],
     "ctc_geglu_bwd": [P, P, I, I, P, P],
     "ctc_cpb_table": [P, P, P, P, P, P, I, I, I, I, P, P],
@@ -49,7 +50,10 @@ SIGNATURES = {
     "ctc_rollout_spatial": [P, I, I, I, P, P],
     "ctc_rollout_temporal": [P, I, I, I, I, P, P],
     "ctc_attn_colmean": [P, I, I, I, P, P],
-    "ctc_colmean": [P, I, I, P, P],
+    "ctc_rollout_fuse": [P, I, I, I, I, I, P, P],
+    "ctc_matmul_f32": [P, P, I, P, P],
+    "ctc_batch_sum": [P, I, L, F, I, P, P],
+    "ctc_colmean": [P, I, I, P, P, P],
     "ctc_gradcam": [P, P, P, I, I, P, P],
     "ctc_upsample_trilinear": [P, I, I, I, P, I, I, I, I, P],
     "ctc_ig_combine": [P, P, L, F, P, P, P],
@@ -61,11 +65,15 @@ SIGNATURES = {
     "ctc_normalize": [P, I, I, I, P, I, I, P, P],
     "ctc_hist16": [P, L, I, ctypes.c_uint, P, P],
     "ctc_ig_finalize": [P, I, I, I, F, F, F, F, I, P, P],
+    "ctc_kth_value": [P, L, L, P, P, P],
+    "ctc_quantile_lerp": [P, P, F, P, P],
+    "ctc_ig_finalize_dev": [P, I, I, I, P, P, I, P, P],
     "ctc_occlusion_heatmap": [P, P, I, I, I, I, I, I, I, I, I, I, I, I, P, P],
 }
 OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, []),
                  "ctc_launch_count": (ctypes.c_longlong, []), "ctc_vq_num_candidates": (c_int, [c_int]),
-                 "ctc_attention_set_tc_bwd": (c_int, [c_int])}
+                 "ctc_attention_set_tc_bwd": (c_int, [c_int]), "ctc_colmean_ws_floats": (c_int, [c_int, c_int]),
+                 "ctc_kth_value_ws_bytes": (c_int, [])}
 
 EPI_BF16, EPI_F32, EPI_ARGMAX, EPI_GEGLU, EPI_GEGLU_BWD = 0, 1, 2, 3, 4
 GEMM_TCGEN05, GEMM_SIMT = 0, 1

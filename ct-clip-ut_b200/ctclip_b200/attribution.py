@@ -76,10 +76,11 @@ def _world():
 _PINNED: Dict[Tuple[int, torch.dtype, int], torch.Tensor] = {}
 
 
-def to_host(t: torch.Tensor, slot: int = 0) -> torch.Tensor:
+def to_host(t: torch.Tensor, slot: int = 0, view: bool = False) -> torch.Tensor:
     """Device -> host copy of a result map through a cached PINNED staging buffer (a pageable `.cpu()` of a
-    221 MB map runs at a fraction of the PCIe rate).  The returned tensor is a view of the staging buffer: it
-    is valid until the next to_host() call with the same element count, dtype and `slot` — copy it to keep it."""
+    221 MB map runs at a fraction of the PCIe rate).  Returns a tensor the caller OWNS.  view=True skips the
+    host-side copy and returns a view of the staging buffer itself, valid only until the next to_host() call with
+    the same element count, dtype and `slot` — for callers that consume the map at once (np.save)."""
     t = t.detach().contiguous()
     key = (t.numel(), t.dtype, slot)
     buf = _PINNED.get(key)
@@ -90,7 +91,7 @@ def to_host(t: torch.Tensor, slot: int = 0) -> torch.Tensor:
     out = buf.view(t.shape)
     out.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return out
+    return out if view else out.clone()
 
 
 def _minmax(x: torch.Tensor) -> torch.Tensor:
@@ -150,6 +151,30 @@ def quantile_linear(x: torch.Tensor, q: float) -> float:
     if gamma >= 0.5:
         r = np.subtract(b, d * (1 - gamma))
     return float(np.float32(r))
+
+
+def kth_value_dev(x: torch.Tensor, k: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """kth_value with the result left in device memory (fp32 [1]) and no host synchronisation."""
+    ws = torch.empty(_lib.load().ctc_kth_value_ws_bytes() // 8 + 1, dtype=torch.int64, device=x.device)
+    out = out if out is not None else torch.empty(1, device=x.device)
+    call("ctc_kth_value", x, x.numel(), int(k), ws, out, stream_ptr())
+    return out
+
+
+def quantile_linear_dev(x: torch.Tensor, q: float) -> torch.Tensor:
+    """quantile_linear evaluated entirely on the device: fp32 [1], bit-identical to NumPy 2.x (see quantile_linear),
+    nothing read back by the host (the IG post-processing chain stays asynchronous)."""
+    n = x.numel()
+    qf = np.asanyarray(q, dtype=np.float32)
+    vi = (n - 1) * qf
+    prev = int(np.floor(vi))
+    nxt = min(prev + 1, n - 1)
+    gamma = float(np.asanyarray(vi - np.float32(prev), dtype=np.float32))
+    a = kth_value_dev(x, prev)
+    b = kth_value_dev(x, nxt) if gamma > 0 else a
+    out = torch.empty(1, device=x.device)
+    call("ctc_quantile_lerp", a, b, gamma, out, stream_ptr())
+    return out
 
 
 # ------------------------------------------------------------------------------------------- occlusion
@@ -316,37 +341,41 @@ def integrated_gradients(engine: Engine, volume: torch.Tensor, text_latents: tor
                          batch: int = 5, shard_steps: bool = True, rot90: bool = True):
     """visualize_integrated_gradients (visualizations.py:851-901).  The alpha steps are batched, the
     interpolation 1 + alpha (x - 1) is applied inside the patch-embedding load and the per-step gradients
-    are summed on the fly into one [D,H,W] buffer (the reference keeps 50 x 221 MB).  With a process
-    group, steps are sharded over ranks and the partial sums all-reduced (NCCL)."""
+    are summed on the fly into one [D,H,W] buffer (the reference keeps 50 x 221 MB).
+    shard_steps=True: EVERY rank of the default process group must hold the SAME volume; the alpha steps are dealt
+    over the ranks and the partial sums combined with one NCCL reduce to rank 0, which alone runs the
+    post-processing (the other ranks return (None, aux)).  shard_steps=False: this rank attributes its own volume
+    (what the reference does, and what `Visualizations.visualize` needs: its loader hands every rank a different scan).
+    The post-processing chain (relu, min/max, exact 0.90 quantile, ** 0.05, rescale, rot90) runs on the device
+    without a host synchronisation."""
     rank, world = _world() if shard_steps else (0, 1)
     dev = engine.dev
     D, H, W = volume.shape[-3:]
     alphas = torch.linspace(0, 1, steps, device=dev)
-    start, end = shard_range(steps, rank, world, parity=False)
+    mine = np.arange(rank, steps, world)             # round-robin: every rank gets floor or ceil(steps / world)
     gsum = torch.zeros(D, H, W, device=dev)
     scores = torch.zeros(steps, device=dev)
     tl = text_latents[:1]
-    for s in range(start, end, batch):
-        e = min(s + batch, end)
-        ctx = engine.forward(volume, tl, batch=e - s, alpha=alphas[s:e].contiguous(), save=True)
-        scores[s:e] = ctx.sim[:, 0]
+    for s in range(0, len(mine), batch):
+        sel = torch.from_numpy(mine[s:s + batch]).to(dev)
+        ctx = engine.forward(volume, tl, batch=len(sel), alpha=alphas[sel].contiguous(), save=True)
+        scores[sel] = ctx.sim[:, 0]
         engine.backward(ctx, grad_out=gsum, sum_over_batch=True)
         del ctx
     if world > 1:
-        dist.all_reduce(gsum)
-        dist.all_reduce(scores)
+        dist.reduce(gsum, dst=0)
+        dist.reduce(scores, dst=0)
+        if rank != 0:
+            return None, {"scores": scores, "gsum": gsum}
     n = D * H * W
     ig = torch.empty(D, H, W, device=dev)
     mm = torch.tensor([float("inf"), float("-inf")], device=dev)
     call("ctc_ig_combine", volume, gsum, n, 1.0 / steps, ig, mm, stream_ptr())     # relu((x-1) * mean grad)
-    mn, mx = float(mm[0]), float(mm[1])
     pre = torch.empty_like(ig)                                                     # (ig-min)/(max+1e-8)
     call("ctc_normalize", ig, D, H, W, mm, 0, 0, pre, stream_ptr())
-    q = quantile_linear(pre, 0.90)
-    n1max = (mx - mn) / (mx + 1e-8)
-    m3 = (n1max ** 0.05) if n1max >= q and n1max > 0 else 0.0
+    q = quantile_linear_dev(pre, 0.90)
     out = torch.empty((D, W, H) if rot90 else (D, H, W), device=dev)
-    call("ctc_ig_finalize", ig, D, H, W, mn, mx, q, 1.0 / (m3 + 1e-8), int(rot90), out, stream_ptr())
+    call("ctc_ig_finalize_dev", ig, D, H, W, mm, q, int(rot90), out, stream_ptr())
     return out, {"pre_threshold": pre, "q90": q, "scores": scores, "gsum": gsum}
 
 
@@ -361,9 +390,11 @@ def grad_cam(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor) -
     T, H, C = ctx.T, cfg.hw, cfg.dim
     R = T * H * H
 
+    ws = torch.empty(_lib.load().ctc_colmean_ws_floats(R, C), device=engine.dev)
+
     def cam(fa, fb, grad):
         w = torch.empty(C, device=engine.dev)
-        call("ctc_colmean", grad, R, C, w, stream_ptr())
+        call("ctc_colmean", grad, R, C, w, ws, stream_ptr())           # two-stage, fixed order: bit-reproducible
         out = torch.empty(R, device=engine.dev)
         call("ctc_gradcam", fa, fb, w, R, C, out, stream_ptr())
         return out.view(T, H, H)
@@ -388,22 +419,25 @@ def grad_cam(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor) -
 # ------------------------------------------------------------------------------------------- attention maps
 def attention_rollout_maps(engine: Engine, volume: torch.Tensor, text_latents: torch.Tensor):
     """visualize_attention_rollout (visualizations.py:779-841), pre-upsample: spatial [layers*t, h, w]
-    (layer-major stack of single-matrix rollouts), temporal [t, h, w]."""
+    (layer-major stack of single-matrix rollouts), temporal [t, h, w].  The attention kernels emit the head-mean
+    probabilities directly (Engine.attention_fused: 32 MB per spatial layer); the [b, heads, n, n] tensors the
+    reference's hooks retain are never materialised."""
     cfg = engine.cfg
     ctx = engine.forward(volume, text_latents[:1], keep_attn=True)
     T, H = ctx.T, cfg.hw
     n = H * H
     rows = []
     for layer in range(cfg.spatial_depth):
-        probs = engine.attention_probs(ctx, "spatial", layer)              # [T, heads, n, n]
+        fused, _ = engine.attention_fused(ctx, "spatial", layer, fused=True)       # [T, n, n] head mean
         out = torch.empty(T, n, device=engine.dev)
-        call("ctc_rollout_spatial", probs, T, cfg.heads, n, out, stream_ptr())
+        call("ctc_rollout_spatial", fused, T, 1, n, out, stream_ptr())
         rows.append(out.view(T, H, H))
-        del probs
+        del fused
     spatial = normalize(torch.cat(rows, 0).contiguous(), 1)
-    tp = torch.stack([engine.attention_probs(ctx, "temporal", l) for l in range(cfg.temporal_depth)]).contiguous()
+    tp = torch.stack([engine.attention_fused(ctx, "temporal", l, fused=True)[0]
+                      for l in range(cfg.temporal_depth)]).contiguous()            # [L, n, T, T]
     out = torch.empty(n, T, device=engine.dev)
-    call("ctc_rollout_temporal", tp, cfg.temporal_depth, n, cfg.heads, T, out, stream_ptr())
+    call("ctc_rollout_temporal", tp, cfg.temporal_depth, n, 1, T, out, stream_ptr())
     temporal = normalize(out.view(H, H, T).permute(2, 0, 1).contiguous(), 1)
     return spatial, temporal
 
@@ -418,15 +452,10 @@ def raw_attention_maps(engine: Engine, volume: torch.Tensor, text_latents: torch
     n = H * H
     sp, tp = [], []
     for layer in range(cfg.spatial_depth):
-        probs = engine.attention_probs(ctx, "spatial", layer)
-        cm = torch.empty(T, cfg.heads, n, device=engine.dev)
-        call("ctc_attn_colmean", probs, T, cfg.heads, n, cm, stream_ptr())
+        _, cm = engine.attention_fused(ctx, "spatial", layer, colmean=True)        # [T, heads, n]
         sp.append(cm.permute(1, 0, 2).reshape(cfg.heads, T, H, H))
-        del probs
     for layer in range(cfg.temporal_depth):
-        probs = engine.attention_probs(ctx, "temporal", layer)
-        cm = torch.empty(n, cfg.heads, T, device=engine.dev)
-        call("ctc_attn_colmean", probs, n, cfg.heads, T, cm, stream_ptr())
+        _, cm = engine.attention_fused(ctx, "temporal", layer, colmean=True)       # [n, heads, T]
         tp.append(cm.permute(1, 0, 2).reshape(cfg.heads, H, H, T).permute(0, 3, 1, 2))
     norm = lambda v: torch.stack([torch.stack([normalize(v[l][h].contiguous(), 0) for l in range(len(v))])
                                   for h in range(cfg.heads)])
@@ -435,27 +464,28 @@ def raw_attention_maps(engine: Engine, volume: torch.Tensor, text_latents: torch
 
 def attention_rollout(attn_weights_list: Sequence[torch.Tensor], head_fusion="mean", discard_ratio=0.0,
                       use_residual=True) -> torch.Tensor:
-    """Generic Visualizations.attention_rollout (visualizations.py:707-743) kept for API compatibility
-    (any list of [heads, n, n] device tensors; host-level utility, not on the hot path)."""
-    n = attn_weights_list[0].size(-1)
-    result = torch.eye(n, device=attn_weights_list[0].device)
+    """Visualizations.attention_rollout (visualizations.py:707-743) for any list of [heads, n, n] CUDA tensors,
+    every option included (head_fusion 'mean' / 'max', discard_ratio, use_residual), on two kernels per layer:
+    ctc_rollout_fuse (fusion, exact per-row top-k threshold, the two row normalisations) and ctc_matmul_f32
+    (result = attn @ result).  Returns the [n, n] rollout matrix."""
+    if head_fusion not in ("mean", "max"):
+        raise ValueError(f"Unsupported head_fusion: {head_fusion}")
+    first = attn_weights_list[0]
+    if not first.is_cuda:
+        raise RuntimeError("ctclip_b200: attention_rollout runs on CUDA tensors only (there is no CPU path)")
+    n = first.size(-1)
+    result = torch.eye(n, device=first.device)
+    k_keep = n - int(n * discard_ratio) if discard_ratio > 0 else n
     for attn in attn_weights_list:
-        if head_fusion == "mean":
-            attn = attn.mean(dim=0)
-        elif head_fusion == "max":
-            attn = attn.max(dim=0)[0]
-        else:
-            raise ValueError(f"Unsupported head_fusion: {head_fusion}")
-        if discard_ratio > 0:
-            flat = attn.reshape(attn.shape[0], -1)
-            num_discard = int(flat.shape[1] * discard_ratio)
-            thr = flat.topk(flat.shape[1] - num_discard, dim=1)[0].min(dim=1, keepdim=True)[0]
-            attn = torch.where(attn >= thr, attn, torch.zeros_like(attn))
-        attn = attn / (attn.sum(dim=-1, keepdim=True) + 1e-8)
-        if use_residual:
-            attn = attn + torch.eye(attn.size(0), device=attn.device)
-            attn = attn / attn.sum(dim=-1, keepdim=True)
-        result = attn @ result
+        attn = attn.detach().float().contiguous()
+        if attn.dim() != 3 or attn.shape[-2:] != (n, n):
+            raise ValueError(f"attention_rollout: expected [heads, {n}, {n}] matrices, got {tuple(attn.shape)}")
+        a = torch.empty(n, n, device=attn.device)
+        call("ctc_rollout_fuse", attn, attn.shape[0], n, int(head_fusion == "max"), max(k_keep, 1), int(use_residual),
+             a, stream_ptr())
+        nxt = torch.empty(n, n, device=attn.device)
+        call("ctc_matmul_f32", a, result, n, nxt, stream_ptr())
+        result = nxt
     return result
 
 
@@ -506,7 +536,7 @@ class Visualizations:
         return upsample(x, target_shape, rot90=False).cpu().numpy()
 
     def _save(self, path, device_array):
-        np.save(path, to_host(device_array).numpy())
+        np.save(path, to_host(device_array, view=True).numpy())     # consumed at once: no second host copy
 
     def visualize_overlay(self, *a, **k):
         return None  # GIF rendering is out of scope
@@ -534,8 +564,11 @@ class Visualizations:
             self._save(d / f"{scan_name}_temporal.npy", temporal_vol)
 
     def visualize_integrated_gradients(self, image, text_tokens, labels, scan_name, original_scan_path, steps=50):
+        # shard_steps=False: `visualize` feeds this method from the DistributedSampler loader, i.e. every rank holds a
+        # DIFFERENT scan and attributes it alone, as in the reference (sharding the alpha steps here would sum the
+        # gradients of different volumes).  Latency mode for ONE volume: integrated_gradients(shard_steps=True).
         ig, aux = integrated_gradients(self._engine(), image.float().contiguous(), self._text_latents(text_tokens),
-                                       steps=steps, batch=self.ig_batch)
+                                       steps=steps, batch=self.ig_batch, shard_steps=False)
         self.saved_outputs["integrated_gradients"] = aux
         if self.accelerator.is_main_process:
             d = self._results_subdirectory("integrated_gradients")
@@ -556,7 +589,7 @@ class Visualizations:
                                           self._text_latents(text_tokens, text_embeds), patch_size, stride,
                                           self.window_batch, self.parity_sharding, threshold)
         self.saved_outputs["occlusion"] = aux
-        return to_host(heat).numpy() if self.accelerator.is_main_process else None   # view of the pinned staging buffer
+        return to_host(heat).numpy() if self.accelerator.is_main_process else None   # an owned host copy
 
     def visualize_occlusion_sensitivity(self, image, text_tokens, labels, scan_name, original_scan_path,
                                         patch_size=(20, 40, 40), stride=(10, 20, 20), use_text_embeds=False, prompt=""):

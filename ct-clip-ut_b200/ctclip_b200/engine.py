@@ -483,14 +483,45 @@ class Engine:
         self.layernorm_bwd(dx, ctx.x_lin, pl.pe_ln2_w, dlin, False, dlin_bf)
         da = self.gemm(dlin_bf, pl.pe_w_t, self._empty(R, cfg.patch_dim, dtype=bf), EPI_BF16)
         _, _, D, Hv, Wv = ctx.volume.shape
+        if not sum_over_batch:
+            if grad_out is None:
+                grad_out = self._empty(B, 1, D, Hv, Wv)
+            call("ctc_patchify_ln_bwd", ctx.volume, ctx.vol_stride, B, D, Hv, Wv, cfg.temporal_patch_size,
+                 cfg.patch_size, pl.pe_ln1_w, LN_EPS, ctx.alpha, da, grad_out, 0, 1.0, stream_ptr())
+            return grad_out
+        # IG running sum: per-row gradients, then the rows are added in order by one kernel (no floating-point atomics:
+        # the sum does not depend on CTA scheduling and is bit-reproducible).  2 x B x 221 MB of extra traffic per
+        # batch of B steps, ~1 % of the batch's time.
         if grad_out is None:
-            grad_out = (torch.zeros(D, Hv, Wv, device=self.dev) if sum_over_batch
-                        else self._empty(B, 1, D, Hv, Wv))
+            grad_out = torch.zeros(D, Hv, Wv, device=self.dev)
+        rows = self._empty(B, 1, D, Hv, Wv)
         call("ctc_patchify_ln_bwd", ctx.volume, ctx.vol_stride, B, D, Hv, Wv, cfg.temporal_patch_size, cfg.patch_size,
-             pl.pe_ln1_w, LN_EPS, ctx.alpha, da, grad_out, int(sum_over_batch), 1.0, stream_ptr())
+             pl.pe_ln1_w, LN_EPS, ctx.alpha, da, rows, 0, 1.0, stream_ptr())
+        call("ctc_batch_sum", rows, B, D * Hv * Wv, 1.0, 1, grad_out, stream_ptr())
         return grad_out
 
     # ------------------------------------------------------------------ attention probabilities
+    def attention_fused(self, ctx: Ctx, kind: str, layer: int, fused: bool = False, colmean: bool = False,
+                        fusion: str = "mean") -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """The two reductions of `attn` (attention.py:174) the attention-map methods consume, emitted by the kernel
+        without materialising the per-head probabilities: the head-fused matrix (visualizations.py:722-725; spatial
+        [B*T, HW, HW], temporal [B*HW, T, T]) and / or the per-head mean over the query axis (:666,671; spatial
+        [B*T, heads, HW], temporal [B*HW, heads, T])."""
+        cfg = self.cfg
+        H = cfg.hw
+        spatial = kind == "spatial"
+        lc = (ctx.spatial if spatial else ctx.temporal)[layer]
+        lw = (self.plan.spatial if spatial else self.plan.temporal)[layer]
+        n = H * H if spatial else ctx.T
+        n_seq = ctx.B * ctx.T if spatial else ctx.B * H * H
+        fm = self._empty(n_seq, n, n) if fused else None
+        cm = self._empty(n_seq, cfg.heads, n) if colmean else None
+        ws = self._empty(n_seq, cfg.heads, (n + 31) // 32, n) if colmean else None
+        call("ctc_attention_fused_probs", lc.q, cfg.inner, lc.kv, 2 * cfg.inner, lc.lse, ctx.B, ctx.T, H, H, cfg.heads,
+             lw.q_scale, lw.k_scale, cfg.attn_scale, self.plan.bias_table if spatial else None,
+             MODE_SPATIAL if spatial else MODE_TEMPORAL, {"mean": 0, "max": 1}[fusion], fm, cm, ws, stream_ptr())
+        return fm, cm
+
     def attention_probs(self, ctx: Ctx, kind: str, layer: int) -> torch.Tensor:
         """Materialise what Attention.forward returns as `attn` (attention.py:174): spatial ->
         [B*T, heads, HW, HW], temporal -> [B*HW, heads, T, T] (fp32)."""

@@ -81,10 +81,20 @@ def zero_shot(model, dataloader, tokenizer, pathologies: Sequence[str] = PATHOLO
     pred = torch.cat(preds) if preds else torch.empty(0, P, dtype=torch.float64, device=eng.dev)
     targ = torch.cat(targets) if targets else torch.empty(0, P, device=eng.dev)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        # ranks may hold different numbers of rows (an uneven loader split): exchange the counts first, pad to the
+        # longest, gather, trim — what accelerator.gather_for_metrics does for the ragged tail
         w = dist.get_world_size()
-        gp = [torch.empty_like(pred) for _ in range(w)]
-        gt = [torch.empty_like(targ) for _ in range(w)]
-        dist.all_gather(gp, pred)
-        dist.all_gather(gt, targ)
-        pred, targ = torch.cat(gp), torch.cat(gt)
+        counts = torch.zeros(w, dtype=torch.int64, device=eng.dev)
+        counts[dist.get_rank()] = pred.shape[0]
+        dist.all_reduce(counts)
+        counts = [int(c) for c in counts.tolist()]
+        pad = max(counts) if counts else 0
+
+        def gather(t):
+            buf = t.new_zeros(pad, *t.shape[1:])
+            buf[:t.shape[0]] = t
+            parts = [torch.empty_like(buf) for _ in range(w)]
+            dist.all_gather(parts, buf)
+            return torch.cat([p[:c] for p, c in zip(parts, counts)])
+        pred, targ = gather(pred), gather(targ)
     return pred, targ

@@ -130,6 +130,15 @@ int ctc_attention_bwd(const void* q, int64_t ldq, const void* k, const void* v, 
 int ctc_attention_probs(const void* q, int64_t ldq, const void* k, int64_t ldkv, const float* lse, int B, int T,
                         int H, int W, int heads, const float* q_scale, const float* k_scale, float scale,
                         const float* bias_table, int mode, float* probs, void* stream);
+/* What the attention-map methods actually consume of those probabilities, emitted WITHOUT materialising them
+ * (the reference keeps attn [b,heads,n,n] of every layer alive through hooks, visualizations.py:153-186):
+ *   fused   fp32 [n_seq, n, n]      head fusion of visualizations.py:722-725: fusion 0 = mean, 1 = max   (or NULL)
+ *   colmean fp32 [n_seq, heads, n]  per head, the mean over the QUERY axis (visualizations.py:666,671)  (or NULL)
+ * colpart_ws fp32 [n_seq, heads, ceil(n/32), n] scratch (needed with colmean).  Deterministic (no atomics). */
+int ctc_attention_fused_probs(const void* q, int64_t ldq, const void* k, int64_t ldkv, const float* lse, int B, int T,
+                              int H, int W, int heads, const float* q_scale, const float* k_scale, float scale,
+                              const float* bias_table, int mode, int fusion, float* fused, float* colmean,
+                              float* colpart_ws, void* stream);
 
 /* Stand-alone GEGLU (attention.py:38-41) on the grouped layout of the fused epilogues: u bf16 [R, 2*F] in
  * 64-wide groups [32 value | 32 gate] -> h = gelu(gate)*value bf16 [R,F]; the product path uses the fused
@@ -180,12 +189,21 @@ int ctc_latent_sim_bwd(const float* latent, const float* text_latents, const flo
  * temporal: probs of all L layers, each [n_tok, heads, T, T] (layer stride = n_tok*heads*T*T) -> out[n_tok, T]. */
 int ctc_rollout_spatial(const float* probs, int n_slices, int heads, int n, float* out, void* stream);
 int ctc_rollout_temporal(const float* probs, int n_layers, int n_tok, int heads, int T, float* out, void* stream);
+/* The generic Visualizations.attention_rollout (visualizations.py:707-743), one layer at a time:
+ * ctc_rollout_fuse: attn fp32 [heads, n, n] -> A fp32 [n, n]: head fusion (0 mean / 1 max); keep only the k_keep
+ *   largest weights of each row (k_keep = n - int(n * discard_ratio); k_keep = n keeps all); A /= rowsum + 1e-8;
+ *   with use_residual A += I, A /= rowsum.
+ * ctc_matmul_f32: C = A @ B, fp32 [n, n] row-major (result = attn @ result, :741). */
+int ctc_rollout_fuse(const float* attn, int heads, int n, int fusion, int k_keep, int use_residual, float* out,
+                     void* stream);
+int ctc_matmul_f32(const float* A, const float* B, int n, float* C, void* stream);
 /* raw attention (visualizations.py:666,671): out[s, h, j] = mean_i P[s,h,i,j] */
 int ctc_attn_colmean(const float* probs, int n_seq, int heads, int n, float* out, void* stream);
 
 /* Grad-CAM (visualizations.py:933-991): w[c] = mean_r grad[r,c]; cam[r] = relu(sum_c (fa[r,c]-fb[r,c]) w[c])
  * (feature = difference of two saved residual streams; fb may be NULL). */
-int ctc_colmean(const float* g, int R, int C, float* w, void* stream);
+int ctc_colmean_ws_floats(int R, int C);
+int ctc_colmean(const float* g, int R, int C, float* w, float* ws, void* stream);
 int ctc_gradcam(const float* fa, const float* fb, const float* w, int R, int C, float* cam, void* stream);
 
 /* Trilinear upsample, align_corners=False (visualizations.py:289-293), optional fused
@@ -197,7 +215,10 @@ int ctc_upsample_trilinear(const float* in, int d, int h, int w, float* out, int
 int ctc_ig_combine(const float* volume, const float* gsum, int64_t n, float inv_steps, float* ig, float* mm,
                    void* stream);
 
-/* Global min/max of an fp32 array into mm[2] (caller pre-sets {+inf, -inf}). */
+/* dst[i] = (accumulate ? dst[i] : 0) + scale * sum_b src[b, i], batch rows added in order: the running sum over
+ * the alpha steps of integrated gradients (visualizations.py:872,878) without floating-point atomics. */
+int ctc_batch_sum(const float* src, int B, int64_t n, float scale, int accumulate, float* dst, void* stream);
+
 /* CT preprocessing in front of the patch embedding (src/utils/preprocess.py:84-151, model_type "ctclip"), fused:
  * HU rescale slope*x+intercept, trilinear resample (align_corners=False) from (z_spacing, xy_spacing, xy_spacing)
  * to (target_z, target_xy, target_xy), clamp [-1000,1000] / 1000, centre crop / symmetric pad with pad_value to
@@ -208,6 +229,7 @@ int ctc_preprocess_ct(const void* raw, int raw_dtype, int H0, int W0, int D0, in
                       float slope, float intercept, double z_spacing, double xy_spacing, double target_z,
                       double target_xy, int D, int H, int W, float pad_value, float* out, int* resampled_dhw,
                       void* stream);
+/* Global min/max of an fp32 array into mm[2] (caller pre-sets {+inf, -inf}). */
 int ctc_minmax(const float* x, int64_t n, float* mm, void* stream);
 /* Zero-shot scoring (CTClipInference.py:133-145, 171-180): sim fp32 [B, 2P] with the "There is X." logit at
  * column 2j and the "There is no X." logit at 2j+1; out float64 [B, P] = softmax over each pair, first entry. */
@@ -224,10 +246,19 @@ int ctc_normalize(const float* in, int D, int H, int W, const float* mm, int mod
  * np.quantile(., 0.90) of visualizations.py:886: shift 16 = high half, shift 0 = low half of the
  * elements whose high half equals prefix.  hist uint32 [65536] (zeroed by the call). */
 int ctc_hist16(const float* x, int64_t n, int shift, unsigned int prefix, unsigned int* hist, void* stream);
+/* k-th smallest (0-based) element of a non-negative fp32 array, exact, two radix passes, result written to
+ * out_dev: no host round trip.  ws: ctc_kth_value_ws_bytes() bytes of 8-byte aligned scratch. */
+int ctc_kth_value_ws_bytes(void);
+int ctc_kth_value(const float* x, int64_t n, int64_t k, void* ws, float* out_dev, void* stream);
+/* np.quantile's "linear" interpolation between two order statistics in float32: out = lerp(a, b, gamma). */
+int ctc_quantile_lerp(const float* a_dev, const float* b_dev, float gamma, float* out_dev, void* stream);
 /* Integrated-gradients finalisation, second half (visualizations.py:882-901): normalise, zero below the
  * quantile q, ** 0.05, divide by the new max (inv_m3 = 1/(max+1e-8)), optional rot90. */
 int ctc_ig_finalize(const float* ig, int D, int H, int W, float mn, float mx, float q, float inv_m3, int rot90,
                     float* out, void* stream);
+/* The same with min/max (mm_dev[2]) and the quantile (q_dev) read from device memory. */
+int ctc_ig_finalize_dev(const float* ig, int D, int H, int W, const float* mm_dev, const float* q_dev, int rot90,
+                        float* out, void* stream);
 /* Occlusion heat map (visualizations.py:366-367, 390-392, 411-413) from per-window importances on the regular
  * window grid [nd,nh,nw] (window i starts at i*stride); inc uint8 marks evaluated windows; heat = sum/count. */
 int ctc_occlusion_heatmap(const float* imp, const unsigned char* inc, int nd, int nh, int nw, int pd, int ph, int pw,

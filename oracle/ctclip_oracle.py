@@ -108,12 +108,24 @@ def _uniform(gen, shape, bound):
     return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * bound
 
 
-def init_state_dict(cfg: CTConfig = FULL, seed: int = 42) -> Dict[str, Tensor]:
+def fitted_codebook(path=None) -> Tensor:
+    """The fitted-codebook fixture (tests/golden/make_fitted_codebook.py): l2norm(int8 rows * per-row scale),
+    fp32 [1, K, dim].  Decoding is element-wise + one row norm, so every host gets the same bits."""
+    from pathlib import Path
+    path = path or Path(__file__).resolve().parent.parent / "tests" / "golden" / "fitted_codebook.npz"
+    z = np.load(path)
+    cb = torch.from_numpy(z["q"].astype(np.float32)) * torch.from_numpy(z["scale"])[:, None]
+    return (cb / cb.double().norm(dim=-1, keepdim=True).float())[None].contiguous()
+
+
+def init_state_dict(cfg: CTConfig = FULL, seed: int = 42, codebook: str = "random") -> Dict[str, Tensor]:
     """Random-init weights under the reference's state-dict keys
     (shapes per attention.py:45-50,59,112-124, ctvit.py:37-66,
     ctclip.py:62-68).  Scales mimic the PyTorch default initialisers; LayerNorm
     gains / biases and q/k scales are perturbed so that no term is trivially
-    the identity."""
+    the identity.  codebook="fitted" (benchmark configuration only) replaces the random
+    unit-vector codebook by the k-means fit of the encoder's own outputs stored in
+    tests/golden/fitted_codebook.npz — what a trained checkpoint's codebook looks like."""
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, Tensor] = {}
     C, P = cfg.dim, cfg.patch_dim
@@ -161,6 +173,12 @@ def init_state_dict(cfg: CTConfig = FULL, seed: int = 42) -> Dict[str, Tensor]:
         ln(f"{vt}{tname}.norm_out", C, "gamma", "beta", zero_bias=True)
     cb = _uniform(g, (1, cfg.codebook_size, C), 1.0)
     sd[vt + "vq._codebook.embed"] = F.normalize(cb, dim=-1)
+    if codebook == "fitted":
+        fc = fitted_codebook()
+        assert tuple(fc.shape) == (1, cfg.codebook_size, C), "the fitted codebook exists for the FULL config only"
+        sd[vt + "vq._codebook.embed"] = fc
+    elif codebook != "random":
+        raise ValueError(f"unknown codebook {codebook!r}")
     sd[vt + "vq._codebook.initted"] = torch.tensor([True])
     sd[vt + "vq._codebook.cluster_size"] = torch.zeros(1, cfg.codebook_size)
     lin("to_text_latent", cfg.dim_latent, cfg.dim_text, bias=False)
@@ -355,16 +373,19 @@ def vq_cosine(x: Tensor, codebook: Tensor, grad_mode: str = "ste_l2norm",
     x: [b, n, d]; codebook: [1, K, d].  Returns (out [b,n,d], ind [b,n] int64).
     `force_indices` (test aid, not in the reference) overrides the arg-max so that a comparison
     can be conditioned on identical code assignments."""
-    x = x.float()
-    E = codebook[0]
-    xh = l2norm(x)
-    dist = xh @ E.t()
-    ind = dist.argmax(dim=-1) if force_indices is None else force_indices.reshape(x.shape[:-1]).long()
-    q = E[ind]
-    base = xh if grad_mode == "ste_l2norm" else x
-    if grad_mode not in ("ste_l2norm", "ste_raw"):
-        raise ValueError(f"unknown vq_grad_mode {grad_mode}")
-    out = base + (q - base).detach()
+    # the library's codebook forward is decorated `@autocast(enabled=False)` and casts to fp32: the distance GEMM and
+    # the arg-max are fp32 even when the model runs under Accelerate's fp16 autocast (CTClipInference.py:56-63)
+    with torch.autocast(device_type=x.device.type, enabled=False):
+        x = x.float()
+        E = codebook[0].float()
+        xh = l2norm(x)
+        dist = xh @ E.t()
+        ind = dist.argmax(dim=-1) if force_indices is None else force_indices.reshape(x.shape[:-1]).long()
+        q = E[ind]
+        base = xh if grad_mode == "ste_l2norm" else x
+        if grad_mode not in ("ste_l2norm", "ste_raw"):
+            raise ValueError(f"unknown vq_grad_mode {grad_mode}")
+        out = base + (q - base).detach()
     return out, ind
 
 

@@ -19,6 +19,10 @@ Outputs (small, committed):
   full_attrib.npz     real Visualizations.{visualize_grad_cam, visualize_attention_rollout,
                       visualize_attention_grid_gif reductions, visualize_integrated_gradients
                       (3 steps), _compute_occlusion (8 coarse windows)} at the benchmark config
+  occ_row.npz         real CTCLIP.forward scores of 69 reference-size (20,40,40) occlusion windows and of the
+                      64-window (60,120,120) grid, plus the real _compute_occlusion heat map of the latter
+  *_fitted.npz        the same three full-size fixtures on the fitted-codebook checkpoint
+                      (--codebook fitted; see make_fitted_codebook.py)
 """
 from __future__ import annotations
 
@@ -184,10 +188,10 @@ def make_tiny(refs, out: Path):
 
 
 # ----------------------------------------------------------------------------- full forward
-def make_full_forward(refs, out: Path):
+def make_full_forward(refs, out: Path, codebook: str = "random"):
     ref_attention, ref_ctvit, ref_ctclip, ref_vis = refs
     cfg = O.FULL
-    sd = O.init_state_dict(cfg, seed=42)
+    sd = O.init_state_dict(cfg, seed=42, codebook=codebook)
     clip = build_reference_model(ref_ctvit, ref_ctclip, cfg, sd)
     img = O.synthetic_volume(cfg, 0)
     txt = O.synthetic_text_embeds(cfg, 7)
@@ -231,10 +235,62 @@ class _NumpyCapture:
         return np.quantile(a, q, *args, **kw)
 
 
-def make_full_attrib(refs, out: Path, ig_steps: int = 3):
+# Occlusion windows scored for the heat-map parity tests (tests/test_gpu_parity.py):
+#   row: reference-size (20,40,40) windows — one full row of the sweep (all 23 w positions at h = 200) at three
+#        depths, the last one clipped by the end of the volume (frames 22-23)
+#   med: the complete non-overlapping (60,120,120) grid, 4 x 4 x 4 = 64 windows (a sweep the reference runs with
+#        patch_size = stride = (60,120,120))
+OCC_ROW_PATCH = (20, 40, 40)
+OCC_ROW_WINDOWS = [(d, 200, w) for d in (50, 100, 220) for w in range(0, 441, 20)]
+OCC_MED_PATCH = (60, 120, 120)
+
+
+def make_occ_row(refs, out: Path, codebook: str = "random"):
+    """Window scores through the real CTCLIP.forward, exactly as the hot loop of _compute_occlusion runs them
+    (visualizations.py:376-388: clone, fill -1, forward, sim[0, 0]); the `med` heat map is produced by the real
+    `_compute_occlusion` itself."""
     ref_attention, ref_ctvit, ref_ctclip, ref_vis = refs
     cfg = O.FULL
-    sd = O.init_state_dict(cfg, seed=42)
+    sd = O.init_state_dict(cfg, seed=42, codebook=codebook)
+    clip = build_reference_model(ref_ctvit, ref_ctclip, cfg, sd)
+    img = O.synthetic_volume(cfg, 0)
+    txt = O.synthetic_text_embeds(cfg, 7)
+    t0 = time.time()
+    res = {"sd_checksum": sd_checksum(sd), "codebook": np.array(codebook)}
+
+    def score(windows, ps, tag):
+        scores = []
+        with torch.no_grad():
+            for (d, h, w) in windows:
+                occ = img.clone()
+                occ[:, :, d:d + ps[0], h:h + ps[1], w:w + ps[2]] = -1
+                scores.append(float(clip(None, occ, txt)[0][0, 0]))
+                print(f"  {tag} window {(d, h, w)}: {scores[-1]:+.6f}  ({time.time() - t0:.0f} s)", flush=True)
+        return np.array(scores)
+
+    with torch.no_grad():
+        res["orig"] = float(clip(None, img, txt)[0][0, 0])
+        res["base_indices"] = clip.visual_transformer(img, return_only_codebook_ids=True).reshape(-1).numpy().astype(np.int16)
+    res["row_patch"] = np.array(OCC_ROW_PATCH)
+    res["row_windows"] = np.array(OCC_ROW_WINDOWS)
+    res["row_scores"] = score(OCC_ROW_WINDOWS, OCC_ROW_PATCH, "row")
+    med = O.occlusion_windows((cfg.depth_voxels, cfg.image_size, cfg.image_size), OCC_MED_PATCH, OCC_MED_PATCH)
+    res["med_patch"] = np.array(OCC_MED_PATCH)
+    res["med_windows"] = np.array(med)
+    res["med_scores"] = score(med, OCC_MED_PATCH, "med")
+    # the med heat map from the reference's own _compute_occlusion (another 65 forwards): sub-sampled
+    import tempfile
+    vis = ref_vis.Visualizations(clip, FakeAccelerator(), None, None, 1, Path(tempfile.mkdtemp()), "", None)
+    heat = vis._compute_occlusion(img, None, txt, OCC_MED_PATCH, OCC_MED_PATCH, 0.0)
+    res["med_heat_sub"] = np.rot90(heat, k=1, axes=(1, 2))[5::10, 10::20, 10::20].astype(np.float32)
+    np.savez_compressed(out, **res)
+    print("occ_row ->", out, "orig", res["orig"])
+
+
+def make_full_attrib(refs, out: Path, ig_steps: int = 3, codebook: str = "random"):
+    ref_attention, ref_ctvit, ref_ctclip, ref_vis = refs
+    cfg = O.FULL
+    sd = O.init_state_dict(cfg, seed=42, codebook=codebook)
     clip = build_reference_model(ref_ctvit, ref_ctclip, cfg, sd)
     img = O.synthetic_volume(cfg, 0)
     txt = O.synthetic_text_embeds(cfg, 7)
@@ -329,16 +385,22 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--only", default="all")
+    ap.add_argument("--codebook", default="random", choices=["random", "fitted"],
+                    help="fitted: the checkpoint whose codebook is tests/golden/fitted_codebook.npz "
+                         "(make_fitted_codebook.py); writes *_fitted.npz")
     args = ap.parse_args()
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     refs = import_reference(args.ref)
-    if args.only in ("all", "tiny"):
+    sfx = "" if args.codebook == "random" else "_fitted"
+    if args.only in ("all", "tiny") and args.codebook == "random":
         make_tiny(refs, HERE / "tiny_model.npz")
     if args.only in ("all", "full"):
-        make_full_forward(refs, HERE / "full_forward.npz")
+        make_full_forward(refs, HERE / f"full_forward{sfx}.npz", codebook=args.codebook)
     if args.only in ("all", "attrib"):
-        make_full_attrib(refs, HERE / "full_attrib.npz")
+        make_full_attrib(refs, HERE / f"full_attrib{sfx}.npz", codebook=args.codebook)
+    if args.only in ("all", "occrow"):
+        make_occ_row(refs, HERE / f"occ_row{sfx}.npz", codebook=args.codebook)
 
 
 if __name__ == "__main__":

@@ -41,7 +41,10 @@ def test_grad_cam_vs_reference_golden(setup):
         r = pearson(maps[k], ref)
         err = float(np.abs(maps[k].cpu().numpy() - ref).max())
         print(f"[grad-cam {k}] pearson {r:.5f} max abs err {err:.3e}")
-        assert r > 0.99, (k, r)
+        # random-codebook checkpoint: the VQ-CAM is relu(codebook rows . w), i.e. it moves with every flipped near-tie
+        # code (0.7 % of the tokens here); the north-star 0.999 is asserted on the fitted-codebook checkpoint in
+        # tests/test_gpu_parity.py, where the arg-max is as well conditioned as in a trained model
+        assert r > (0.99 if k in ("vq", "combined", "spatial") else 0.999), (k, r)
 
 
 def test_rollout_and_raw_attention_vs_reference_golden(setup):
@@ -75,10 +78,11 @@ def test_integrated_gradients_vs_reference_golden(setup):
     r = pearson(sub, gold["ig_pre_sub"])
     # the exact device quantile agrees with numpy on OUR map
     q_np = float(np.quantile(pre.cpu().numpy(), 0.90))
+    aux["q90"] = float(aux["q90"])                 # a device scalar: the post-processing chain never syncs with the host
     print(f"[IG] pre-threshold pearson {r:.5f}; q90 ours {aux['q90']:.6e} numpy-on-ours {q_np:.6e} "
           f"reference {float(gold['ig_q90']):.6e}; nonzero {int((out > 0).sum())} vs {int(gold['ig_final_nonzero'])}")
     assert aux["q90"] == q_np                      # exact device quantile == numpy, bit for bit
-    assert r > 0.98
+    assert r > 0.999
     nz = int((out > 0).sum())
     assert abs(nz - int(gold["ig_final_nonzero"])) < 0.02 * int(gold["ig_final_nonzero"])
     # final map == reference post-processing applied to OUR pre-threshold map (bit-level formula check)

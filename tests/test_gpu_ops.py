@@ -515,7 +515,8 @@ def test_rollout_colmean_gradcam(lib):
     R, C = 13824, 512
     g, fa, fb = rnd(R, C, seed=3), rnd(R, C, seed=4), rnd(R, C, seed=5)
     w = torch.empty(C, device=dev())
-    lib.call("ctc_colmean", g, R, C, w, lib.stream_ptr())
+    ws = torch.empty(lib.load().ctc_colmean_ws_floats(R, C), device=dev())
+    lib.call("ctc_colmean", g, R, C, w, ws, lib.stream_ptr())
     assert relerr(w, g.mean(dim=0)) < 1e-3
     cam = torch.empty(R, device=dev())
     lib.call("ctc_gradcam", fa, fb, w, R, C, cam, lib.stream_ptr())
