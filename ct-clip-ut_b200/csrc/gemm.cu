@@ -1,7 +1,7 @@
 // Dense bf16 GEMM family for the CTViT linears:  C[M,N] = A[M,K] · B[N,K]ᵀ  (fp32 accumulate).
 //
 // sm_100a design: persistent, warp-specialised kernel, one CTA per SM.
-//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, 4-stage mbarrier ring)
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, mbarrier ring: 4 stages, 6 in pair mode)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma kind::f16, M=128, N=BN, K=16)
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
 //   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global); a warp may
@@ -12,6 +12,17 @@
 // MMAs of tile i+1.  Both operands are K-major ("row-major [rows, K]"), which is exactly the
 // nn.Linear weight layout [out_features, in_features] (reference: src/utils/attention.py:47,49,
 // 119-120,124; src/utils/ctvit.py:50; src/models/ctclip.py:62-63).
+//
+// Pair mode (CG = 2, the default for 256-wide tiles): the two CTAs of a 2-CTA cluster sit on the two SMs of a TPC
+// and compute ONE 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256: 128 accumulator rows in each CTA's TMEM).
+// Each CTA stages its own 128 A rows and only HALF of the B tile (128 of the 256 weight rows); the tensor core
+// reads the other half from the peer's shared memory.  Per SM and 64-deep k-block that is 32 KB from L2 instead
+// of 48 KB for the same 4 MMAs — ncu showed the K <= 512 launches (to_q, to_kv, FF1 + GEGLU, dh) bound by exactly
+// that L2 -> SM operand stream at 48-54 % tensor-pipe activity (chip-wide L2 read cap / 148 SMs ~ 43 B/clk against
+// 94 B/clk demanded) — and the smaller stage buys a 6-deep ring.  Protocol: both producers signal the LEADER's full
+// barrier (TMA .cta_group::2 completion on a peer mbarrier), the leader's elected thread issues the MMAs and
+// multicasts its commits to the empty / accumulator-full barriers of both CTAs, the peer's epilogue warps arrive
+// remotely on the leader's accumulator-empty barrier.
 //
 // A plain SIMT kernel with the same epilogues (gemm_simt) is kept as a bring-up / cross-check
 // comparator for tests; the product path always uses the tcgen05 kernel.
@@ -24,7 +35,6 @@ namespace ctc {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int kStages = 4;
 static constexpr int kEpiWarps = 8;
 static constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 
@@ -35,17 +45,18 @@ struct GemmArgs {
     const float* bias;  // [N] or null
     const float* resid; // fp32 [M, ldr] or null (may alias out)
     long long ldr;
-    void* aux;          // EPI_GEGLU: optional u bf16 [M, N] out; EPI_GEGLU_BWD: u bf16 [M, 2N] in
+    void* aux;          // EPI_GEGLU: optional adjoint factors [a | b] bf16 [M, N] out; EPI_GEGLU_BWD: the same [M, 2N] in
     long long ldaux;
     float* top2_val;    // EPI_ARGMAX: [M, n_tiles*2]
     int* top2_idx;
     int n_tiles_n;
 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmSmem {
+    static constexpr int kStages = CG == 2 ? 6 : 4;
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = (BN / CG) * BK * 2;          // pair mode: each CTA stages half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStageOut = kEpiWarps * 4096;       // epilogue staging: per warp 32 rows x 128 B
     static constexpr int kOutOffset = kStages * kStageBytes;
@@ -220,11 +231,16 @@ struct Top2 {
     }
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmArgs g) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, CG>;
+    constexpr int kStages = S::kStages;
+    constexpr int TM = BM * CG;                                   // rows of one tile (pair mode: 256)
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
+    const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // tile-scheduling unit: CTA or CTA pair
+    const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
@@ -235,7 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tiles_m = (g.M + BM - 1) / BM;
+    const int tiles_m = (g.M + TM - 1) / TM;
     const int tiles_n = (g.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int k_blocks = (g.K + BK - 1) / BK;
@@ -247,12 +263,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * CG); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+    if (warp == 2) {
+        if constexpr (CG == 2) tmem_alloc_cg2<kTmemCols>(tmem_ptr);
+        else tmem_alloc<kTmemCols>(tmem_ptr);
+    }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();      // the peer's barriers must be initialised before anything signals them
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -260,26 +280,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += n_units) {
                 const int tm = tile / tiles_n, tn = tile % tiles_n;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * S::kStageBytes;
                     uint8_t* sb = sa + S::kABytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
-                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                    if constexpr (CG == 2) {
+                        // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
+                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+                        tma_load_2d_cg2(sa, &tmap_a, fb, kb * BK, tm * TM + (int)rank * BM);
+                        tma_load_2d_cg2(sb, &tmap_b, fb, kb * BK, tn * BN + (int)rank * (BN / 2));
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(TM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += n_units) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
@@ -293,13 +321,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr>>4) field
-                        umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                    (kb > 0 || k > 0) ? 1u : 0u);
+                        if constexpr (CG == 2)
+                            umma_f16_ss_cg2(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                            (kb > 0 || k > 0) ? 1u : 0u);
+                        else
+                            umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                        (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    // frees the smem slot (of both CTAs in pair mode) once these MMAs retire
+                    if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs)
+                if constexpr (CG == 2) umma_commit_cg2(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -310,13 +344,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
         const int cbeg = eh * kColsPerWarp, cend = cbeg + kColsPerWarp;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = unit; tile < num_tiles; tile += n_units) {
             const int tm = tile / tiles_n, tn = tile % tiles_n;
+            const int rbase = tm * TM + (int)rank * BM;          // first row of this CTA's 128 accumulator rows
             if constexpr (EPI == CTC_EPI_F32) {
                 // While this tile's MMAs run, pull the residual rows this warp will add (32 rows x its columns, fp32)
                 // into L2: the epilogue's loads then hit L2 instead of waiting on HBM with only 4 KB in flight per warp.
                 if (g.resid) {
-                    const int prow = tm * BM + ew * 32 + lane;
+                    const int prow = rbase + ew * 32 + lane;
                     const int pcol = tn * BN + cbeg;
                     if (prow < g.M) {
                         const float* pr = g.resid + (long long)prow * g.ldr + pcol;
@@ -328,7 +363,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             if constexpr (EPI == CTC_EPI_GEGLU_BWD) {
                 // same idea for the saved pre-activation u the adjoint reads (bf16, 2 x this warp's columns per row)
-                const int prow = tm * BM + ew * 32 + lane;
+                const int prow = rbase + ew * 32 + lane;
                 const int pcol = 2 * (tn * BN + cbeg);
                 if (prow < g.M) {
                     const __nv_bfloat16* pu = reinterpret_cast<const __nv_bfloat16*>(g.aux) + (long long)prow * g.ldaux + pcol;
@@ -339,10 +374,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const int row = tm * BM + ew * 32 + lane;
+            const int row = rbase + ew * 32 + lane;
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
             uint8_t* stage = smem + S::kOutOffset + (warp - 4) * 4096;
-            const int row0 = tm * BM + ew * 32;
+            const int row0 = rbase + ew * 32;
             if constexpr (EPI == CTC_EPI_ARGMAX) {
                 // four independent trackers break the 256-long dependent compare chain
                 Top2 t2[4];
@@ -382,7 +417,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             } else if constexpr (EPI == CTC_EPI_GEGLU) {
                 // columns come in 64-wide groups [32 value | 32 gate] (weights interleaved at plan time):
-                // h = gelu(gate) * value (attention.py:38-41) straight from the fp32 accumulators
+                // h = gelu(gate) * value (attention.py:38-41) straight from the fp32 accumulators.  For the backward
+                // pass the epilogue saves, in the same [32 | 32] layout, the two ADJOINT FACTORS instead of the
+                // pre-activation:  a = gelu(gate) = d h / d value,  b = value * gelu'(gate) = d h / d gate  (one exp
+                // gives both the cdf and the pdf), so that the adjoint is two multiplies per element and fits the
+                // dh GEMM's epilogue (EPI_GEGLU_BWD) instead of a stand-alone HBM pass over u, dh and du.
                 __nv_bfloat16* hout = reinterpret_cast<__nv_bfloat16*>(g.out);
                 __nv_bfloat16* uout = reinterpret_cast<__nv_bfloat16*>(g.aux);
 #pragma unroll 1
@@ -393,25 +432,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     tmem_ld_32x32b_x32(taddr + c, xv);
                     tmem_ld_32x32b_x32(taddr + c + 32, gv);
                     tmem_ld_wait();
+                    uint32_t hk[16];
                     if (uout) {
                         uint32_t pk[32];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            pk[j] = pack_bf16(__uint_as_float(xv[2 * j]), __uint_as_float(xv[2 * j + 1]));
-                            pk[16 + j] = pack_bf16(__uint_as_float(gv[2 * j]), __uint_as_float(gv[2 * j + 1]));
+                            const float x0 = __uint_as_float(xv[2 * j]), x1 = __uint_as_float(xv[2 * j + 1]);
+                            const float g0 = __uint_as_float(gv[2 * j]), g1 = __uint_as_float(gv[2 * j + 1]);
+                            float c0, p0, c1, p1;
+                            gelu_parts(g0, c0, p0);
+                            gelu_parts(g1, c1, p1);
+                            const float a0 = g0 * c0, a1 = g1 * c1;
+                            hk[j] = pack_bf16(a0 * x0, a1 * x1);
+                            pk[j] = pack_bf16(a0, a1);
+                            pk[16 + j] = pack_bf16(x0 * fmaf(g0, p0, c0), x1 * fmaf(g1, p1, c1));
                         }
                         epilogue_bf16_staged(g, stage, row0, col0, lane, pk, uout, g.ldaux);
-                    }
-                    uint32_t hk[16];
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        hk[j] = pack_bf16(gelu_erf(__uint_as_float(gv[2 * j])) * __uint_as_float(xv[2 * j]),
-                                          gelu_erf(__uint_as_float(gv[2 * j + 1])) * __uint_as_float(xv[2 * j + 1]));
+                        for (int j = 0; j < 16; ++j)
+                            hk[j] = pack_bf16(gelu_erf(__uint_as_float(gv[2 * j])) * __uint_as_float(xv[2 * j]),
+                                              gelu_erf(__uint_as_float(gv[2 * j + 1])) * __uint_as_float(xv[2 * j + 1]));
+                    }
                     epilogue_bf16_staged32(g, stage, row0, col0 / 2, lane, hk, hout, g.ldc);
                 }
             } else if constexpr (EPI == CTC_EPI_GEGLU_BWD) {
-                // acc = dh chunk (32 columns); u = [value | gate] of the same columns is one 128-byte row segment:
-                // du_value = gelu(gate) * dh, du_gate = value * gelu'(gate) * dh, written back in the same layout
+                // acc = dh chunk (32 columns); aux = the saved adjoint factors [a | b] of the same columns, one 128-byte
+                // row segment: du_value = a * dh, du_gate = b * dh, written back in the same grouped layout
                 const __nv_bfloat16* uin = reinterpret_cast<const __nv_bfloat16*>(g.aux);
                 __nv_bfloat16* duout = reinterpret_cast<__nv_bfloat16*>(g.out);
 #pragma unroll 1
@@ -425,15 +472,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     uint32_t pk[32];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const uint4 xa = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u));
-                        const uint4 ga = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u + 4));
-                        const uint32_t xs[4] = {xa.x, xa.y, xa.z, xa.w}, gs[4] = {ga.x, ga.y, ga.z, ga.w};
+                        const uint4 aa = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u));
+                        const uint4 ba = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u + 4));
+                        const uint32_t as[4] = {aa.x, aa.y, aa.z, aa.w}, bs[4] = {ba.x, ba.y, ba.z, ba.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float2 xf = unpack_bf16(xs[e]), gf = unpack_bf16(gs[e]);
+                            const float2 af = unpack_bf16(as[e]), bf = unpack_bf16(bs[e]);
                             const float d0 = __uint_as_float(dh[u * 8 + 2 * e]), d1 = __uint_as_float(dh[u * 8 + 2 * e + 1]);
-                            pk[u * 4 + e] = pack_bf16(gelu_erf(gf.x) * d0, gelu_erf(gf.y) * d1);
-                            pk[16 + u * 4 + e] = pack_bf16(xf.x * gelu_erf_grad(gf.x) * d0, xf.y * gelu_erf_grad(gf.y) * d1);
+                            pk[u * 4 + e] = pack_bf16(af.x * d0, af.y * d1);
+                            pk[16 + u * 4 + e] = pack_bf16(bf.x * d0, bf.y * d1);
                         }
                     }
                     __syncwarp();
@@ -487,15 +534,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                // pair mode: the leader's MMA issuer waits for the epilogue warps of BOTH CTAs
+                if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();      // neither CTA may leave while the pair's MMAs / remote arrives are in flight
+    else __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc<kTmemCols>(tmem_base);
+        if constexpr (CG == 2) tmem_dealloc_cg2<kTmemCols>(tmem_base);
+        else tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -576,19 +629,30 @@ int num_sms() {
     return g_num_sms[dev];
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, CG>;
     static bool configured_dev[kMaxDevices] = {};
     bool& configured = configured_dev[current_device()];
     if (!configured) {
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             S::kTotal));
         configured = true;
     }
-    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, g);
+    const int tiles = ((g.M + BM * CG - 1) / (BM * CG)) * ((g.N + BN - 1) / BN);
+    const int units = num_sms() / CG;                       // CTAs, or CTA pairs (one pair per TPC)
+    const int grid = (tiles < units ? tiles : units) * CG;
+    if constexpr (CG == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = S::kTotal; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CTC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, ta, tb, g));
+    } else {
+        gemm_tcgen05_kernel<BN, EPI, CG><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, g);
+    }
     CTC_LAUNCH_CHECK();
     return 0;
 }
@@ -601,7 +665,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
     g.M = M; g.N = N; g.K = K; g.out = out; g.ldc = ldc; g.bias = bias; g.resid = resid; g.ldr = ldr;
     g.top2_val = top2_val; g.top2_idx = top2_idx; g.aux = aux; g.ldaux = ldaux;
     if (epi == CTC_EPI_GEGLU || epi == CTC_EPI_GEGLU_BWD) {
-        CTC_REQUIRE(impl == CTC_GEMM_TCGEN05, "gemm: the fused GEGLU epilogues exist only in the tcgen05 kernel");
+        CTC_REQUIRE(impl != CTC_GEMM_SIMT, "gemm: the fused GEGLU epilogues exist only in the tcgen05 kernels");
         CTC_REQUIRE(N % 64 == 0 && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                     (!aux || (ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0)),
                     "gemm: GEGLU epilogues need N %% 64 == 0 and 16-byte aligned bf16 rows (N=%d)", N);
@@ -624,25 +688,29 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
     // 191 us for 128-wide tiles - twice the MMA work per byte staged through shared memory.)
     const bool bn256 = (epi == CTC_EPI_ARGMAX) || (N % 256 == 0) || (N % 128 != 0) || (N >= 512);
     const int BNsel = bn256 ? 256 : 128;
+    // CTA pairs (cta_group::2, 256 x 256 tiles) for every 256-wide case unless the caller asks for the single-CTA kernel
+    // (CTC_GEMM_PAIR=0 in the environment switches the default back to single CTAs: an A/B measurement aid)
+    static const int pair_env = [] { const char* e = getenv("CTC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+    const bool pair = bn256 && impl != CTC_GEMM_TCGEN05_1CTA && pair_env && (num_sms() % 2 == 0);
     g.n_tiles_n = (N + BNsel - 1) / BNsel;
     CUtensorMap ta, tb;
     if (int e = make_tmap_bf16(&ta, A, M, K, lda, BM)) return e;
-    if (int e = make_tmap_bf16(&tb, B, N, K, ldb, BNsel)) return e;
+    if (int e = make_tmap_bf16(&tb, B, N, K, ldb, pair ? BNsel / 2 : BNsel)) return e;
+#define CTC_GEMM_DISPATCH(EPI)                                                                                   \
+    return pair ? launch_tc<256, EPI, 2>(ta, tb, g, st)                                                          \
+                : (bn256 ? launch_tc<256, EPI, 1>(ta, tb, g, st) : launch_tc<128, EPI, 1>(ta, tb, g, st))
     switch (epi) {
-        case CTC_EPI_BF16:
-            return bn256 ? launch_tc<256, CTC_EPI_BF16>(ta, tb, g, st) : launch_tc<128, CTC_EPI_BF16>(ta, tb, g, st);
-        case CTC_EPI_F32:
-            return bn256 ? launch_tc<256, CTC_EPI_F32>(ta, tb, g, st) : launch_tc<128, CTC_EPI_F32>(ta, tb, g, st);
-        case CTC_EPI_GEGLU:
-            return bn256 ? launch_tc<256, CTC_EPI_GEGLU>(ta, tb, g, st) : launch_tc<128, CTC_EPI_GEGLU>(ta, tb, g, st);
-        case CTC_EPI_GEGLU_BWD:
-            return bn256 ? launch_tc<256, CTC_EPI_GEGLU_BWD>(ta, tb, g, st) : launch_tc<128, CTC_EPI_GEGLU_BWD>(ta, tb, g, st);
+        case CTC_EPI_BF16: CTC_GEMM_DISPATCH(CTC_EPI_BF16);
+        case CTC_EPI_F32: CTC_GEMM_DISPATCH(CTC_EPI_F32);
+        case CTC_EPI_GEGLU: CTC_GEMM_DISPATCH(CTC_EPI_GEGLU);
+        case CTC_EPI_GEGLU_BWD: CTC_GEMM_DISPATCH(CTC_EPI_GEGLU_BWD);
         case CTC_EPI_ARGMAX:
             CTC_REQUIRE(top2_val && top2_idx, "gemm: arg-max epilogue needs top2 buffers");
-            return launch_tc<256, CTC_EPI_ARGMAX>(ta, tb, g, st);
+            return pair ? launch_tc<256, CTC_EPI_ARGMAX, 2>(ta, tb, g, st) : launch_tc<256, CTC_EPI_ARGMAX, 1>(ta, tb, g, st);
         default:
             CTC_REQUIRE(false, "gemm: unknown epilogue %d", epi);
     }
+#undef CTC_GEMM_DISPATCH
     return 0;
 }
 

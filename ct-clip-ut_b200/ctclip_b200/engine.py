@@ -32,7 +32,8 @@ class LayerCtx:
     kv: torch.Tensor = None      # bf16 [R, 2*inner]
     o: torch.Tensor = None       # bf16 [R, inner]
     lse: torch.Tensor = None     # fp32 [R, heads]
-    u: torch.Tensor = None       # bf16 [R, 2*FP]  FF pre-activation
+    u: torch.Tensor = None       # bf16 [R, 2*FP]  GEGLU adjoint factors [gelu(gate) | value*gelu'(gate)] (tcgen05 path)
+                                 #                 or the FF pre-activation [value | gate] (SIMT comparator path)
 
 
 @dataclass
@@ -130,7 +131,6 @@ class Engine:
         self.cfg = plan.cfg
         self.dev = plan.device
         self.gemm_impl = gemm_impl
-        self.fuse_geglu_bwd = False
         self.attn_tc = True          # spatial attention forward on tcgen05/TMEM (ctc_attention_fwd_tc)
         self._row_cap = 0
 
@@ -210,11 +210,11 @@ class Engine:
         # x = ff(x) + x                                                    attention.py:43-51, 334
         xn2 = xn  # reuse
         self.layernorm(x2, lw.ff_ln_w, lw.ff_ln_b, y_bf16=xn2)
-        # Linear(dim, 2*inner) + GEGLU fused in the GEMM epilogue; the pre-activation u is only written when
-        # the backward pass will need it
+        # Linear(dim, 2*inner) + GEGLU fused in the GEMM epilogue; the adjoint factors u = [gelu(gate) | value *
+        # gelu'(gate)] are only written when a backward pass will follow
         u = self._empty(R, 2 * FP, dtype=bf) if save else None
         hff = self._empty(R, FP, dtype=bf)
-        if self.gemm_impl == _lib.GEMM_TCGEN05:
+        if self.gemm_impl != _lib.GEMM_SIMT:
             self.gemm(xn2, lw.w1, hff, _lib.EPI_GEGLU, aux=u)
         else:   # SIMT comparator path (tests): plain GEMM + stand-alone GEGLU
             u = self.gemm(xn2, lw.w1, self._empty(R, 2 * FP, dtype=bf), EPI_BF16)
@@ -399,14 +399,13 @@ class Engine:
         if capture is not None:
             capture[tag + "_ff"] = dx3.clone()          # d/d(ff output)  == grad of x3
         # ---- FeedForward
-        # dh = dx3 @ W2, then the GEGLU adjoint as its own HBM-bound pass.  (A fused GEMM epilogue exists,
-        # EPI_GEGLU_BWD, but evaluating gelu / gelu' per element and re-reading u in the epilogue warps makes the
-        # GEMM epilogue-bound: 779 us fused against 160 + 243 us for GEMM + stand-alone pass on B200 with eight
-        # epilogue warps and the L2 prefetch of u - so it is not used.)
+        # du = GEGLU'(u) * (dx3 @ W2): the adjoint is fused into the dh GEMM's epilogue.  The forward saved the two
+        # adjoint factors instead of the pre-activation, so the epilogue does two multiplies per element (round 1
+        # evaluated erf / erf' there and was epilogue-bound: 779 us fused against 160 + 243 us for GEMM + pass).
         du = self._empty(R, 2 * FP, dtype=bf)
-        if self.fuse_geglu_bwd and self.gemm_impl == _lib.GEMM_TCGEN05:
+        if self.gemm_impl != _lib.GEMM_SIMT:
             self.gemm(dx3_bf, lw.w2_t, du, _lib.EPI_GEGLU_BWD, aux=lc.u)
-        else:
+        else:   # SIMT comparator path (tests): lc.u holds the pre-activation
             dh = self.gemm(dx3_bf, lw.w2_t, self._empty(R, FP, dtype=bf), EPI_BF16)
             call("ctc_geglu_bwd", lc.u, dh, R, FP, du, stream_ptr())
             del dh

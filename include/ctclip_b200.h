@@ -30,8 +30,9 @@ extern "C" {
 
 /* GEMM epilogues */
 enum { CTC_EPI_BF16 = 0, CTC_EPI_F32 = 1, CTC_EPI_ARGMAX = 2, CTC_EPI_GEGLU = 3, CTC_EPI_GEGLU_BWD = 4 };
-/* GEMM implementation: tcgen05 is the product path; SIMT is a test comparator */
-enum { CTC_GEMM_TCGEN05 = 0, CTC_GEMM_SIMT = 1 };
+/* GEMM implementation: tcgen05 is the product path (CTA pairs / cta_group::2 wherever the tile is 256 wide);
+ * TCGEN05_1CTA forces the single-CTA (cta_group::1) kernel and SIMT is a plain comparator - both for tests. */
+enum { CTC_GEMM_TCGEN05 = 0, CTC_GEMM_SIMT = 1, CTC_GEMM_TCGEN05_1CTA = 2 };
 /* sequence mode of the factorised transformer (ctvit.py:94-101) */
 enum { CTC_MODE_SPATIAL = 0, CTC_MODE_TEMPORAL = 1 };
 
@@ -45,9 +46,11 @@ long long ctc_launch_count(void);
 /* C[M,N] = A[M,K] * B[N,K]^T, bf16 operands (row strides lda/ldb elements), fp32 accumulate.
  * epi BF16: out bf16 [M,ldc]; F32: out fp32 = acc (+bias[N]) (+resid fp32 [M,ldr], may alias out).
  * epi GEGLU (FeedForward, attention.py:38-49): the N output columns are 64-wide groups [32 value | 32 gate]
- *   (weight rows interleaved by the caller); out = gelu(gate)*value bf16 [M, N/2]; aux (optional) receives
- *   the pre-activation u bf16 [M, N] (stride ldaux) for the backward pass.
- * epi GEGLU_BWD: acc = dh [M,N]; aux = saved u bf16 [M, 2N]; out = du bf16 [M, 2N] in the same grouped layout.
+ *   (weight rows interleaved by the caller); out = gelu(gate)*value bf16 [M, N/2]; aux (optional, stride ldaux)
+ *   receives, in the same grouped layout, the ADJOINT FACTORS the backward pass needs, bf16 [M, N]:
+ *   [32 a | 32 b] with a = gelu(gate) = dh/dvalue and b = value * gelu'(gate) = dh/dgate.
+ * epi GEGLU_BWD: acc = dh [M,N]; aux = those factors bf16 [M, 2N]; out = du bf16 [M, 2N] = [a*dh | b*dh], the
+ *   gradient w.r.t. the pre-activation in the grouped layout (two multiplies per element: fits the epilogue).
  * Replaces every nn.Linear / einsum on the path: attention.py:47,49,142,182; ctvit.py:50. */
 int ctc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldc, int M, int N,
                   int K, int epi, const float* bias, const float* resid, int64_t ldr, void* aux, int64_t ldaux,

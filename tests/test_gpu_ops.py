@@ -34,10 +34,10 @@ def relerr(a, b):
 
 
 # --------------------------------------------------------------------------------------- GEMM
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])        # 0 = tcgen05 CTA pairs (product), 1 = SIMT, 2 = tcgen05 single CTA
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 200, 136), (1000, 512, 512), (2048, 1408, 512),
                                    (13824, 512, 4000), (4096, 256, 512), (1536, 2816, 512), (512, 4000, 512),
-                                   (777, 64, 256), (256, 512, 2816)])
+                                   (777, 64, 256), (256, 512, 2816), (129, 256, 512), (38016, 512, 512)])
 def test_gemm_bf16_out(lib, impl, M, N, K):
     a = rnd(M, K, seed=1, dtype=torch.bfloat16)
     w = rnd(N, K, seed=2, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
@@ -49,8 +49,8 @@ def test_gemm_bf16_out(lib, impl, M, N, K):
     assert relerr(out, ref) < 1e-2
 
 
-@pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("M,N,K", [(256, 512, 256), (999, 512, 1408), (13824, 512, 256), (130, 64, 256)])
+@pytest.mark.parametrize("impl", [0, 1, 2])        # 0 = tcgen05 CTA pairs (product), 1 = SIMT, 2 = tcgen05 single CTA
+@pytest.mark.parametrize("M,N,K", [(256, 512, 256), (999, 512, 1408), (13824, 512, 256), (130, 64, 256), (300, 256, 512), (4161, 1408, 512)])
 def test_gemm_f32_bias_resid(lib, impl, M, N, K):
     a = rnd(M, K, seed=3, dtype=torch.bfloat16)
     w = rnd(N, K, seed=4, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
@@ -347,8 +347,14 @@ def test_gemm_fused_geglu_epilogues(lib, M, Fp, K):
     u = torch.full((M, 2 * Fp), float("nan"), device=dev(), dtype=torch.bfloat16)
     lib.call("ctc_gemm_bf16", a, K, w, K, h, Fp, M, 2 * Fp, K, lib.EPI_GEGLU, None, None, 0, u, 2 * Fp, 0, lib.stream_ptr())
     xv, xg = a.float() @ wv.float().t(), a.float() @ wg.float().t()
-    assert relerr(u, _group(xv, xg)) < 1e-2
+    # aux = the adjoint factors [a | b]: a = gelu(gate) = dh/dvalue, b = value * gelu'(gate) = dh/dgate
+    xg_ = xg.clone().requires_grad_()
+    (dgelu,) = torch.autograd.grad(F.gelu(xg_).sum(), xg_)
+    assert relerr(u, _group(F.gelu(xg), xv * dgelu)) < 1e-2
     assert relerr(h, F.gelu(xg) * xv) < 1e-2
+    h1, u1 = torch.empty_like(h), torch.empty_like(u)          # single-CTA kernel: same accumulation order, same bits
+    lib.call("ctc_gemm_bf16", a, K, w, K, h1, Fp, M, 2 * Fp, K, lib.EPI_GEGLU, None, None, 0, u1, 2 * Fp, 2, lib.stream_ptr())
+    assert torch.equal(h, h1) and torch.equal(u, u1)
     h2 = torch.empty_like(h)                                   # without the pre-activation output
     lib.call("ctc_gemm_bf16", a, K, w, K, h2, Fp, M, 2 * Fp, K, lib.EPI_GEGLU, None, None, 0, None, 0, 0, lib.stream_ptr())
     assert torch.equal(h, h2)
@@ -360,8 +366,7 @@ def test_gemm_fused_geglu_epilogues(lib, M, Fp, K):
     lib.call("ctc_gemm_bf16", d, Kd, w2t, Kd, du, 2 * Fp, M, Fp, Kd, lib.EPI_GEGLU_BWD, None, None, 0, u, 2 * Fp, 0,
              lib.stream_ptr())
     dh = d.float() @ w2t.float().t()
-    uf = u.float().view(M, Fp // 32, 2, 32)
-    xs, gs = uf[:, :, 0].reshape(M, Fp).requires_grad_(), uf[:, :, 1].reshape(M, Fp).requires_grad_()
+    xs, gs = xv.clone().requires_grad_(), xg.clone().requires_grad_()
     dx_ref, dg_ref = torch.autograd.grad(F.gelu(gs) * xs, [xs, gs], dh)
     assert relerr(du, _group(dx_ref, dg_ref)) < 1.5e-2
 

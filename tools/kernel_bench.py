@@ -42,11 +42,15 @@ if what in ("gemm", "all"):
         else:
             out = torch.empty(R, N, device=dev, dtype=bf if epi == L.EPI_BF16 else torch.float32)
         res = rnd(R, N) if resid else None
-        def f():
-            L.call("ctc_gemm_bf16", a, K, w, K, out, out.stride(0), R, N, K, epi, None, res, N if resid else 0, None, 0, 0,
+        def f(impl=0):
+            L.call("ctc_gemm_bf16", a, K, w, K, out, out.stride(0), R, N, K, epi, None, res, N if resid else 0, None, 0, impl,
                    L.stream_ptr())
-        us = timeit(f)
-        print(f"  gemm {name:18s} N={N:5d} K={K:5d}: {us:8.1f} us  {2.0 * R * N * K / us / 1e6:8.1f} TFLOP/s")
+        us = timeit(f)                       # CTA pairs (cta_group::2), the product path
+        us1 = timeit(lambda: f(2))           # single-CTA kernel (cta_group::1)
+        usb = timeit(lambda: torch.matmul(a, w.t()))     # cuBLAS, bare bf16 GEMM (no epilogue work)
+        fl = 2.0 * R * N * K / 1e6
+        print(f"  gemm {name:18s} N={N:5d} K={K:5d}: pair {us:8.1f} us {fl / us:7.1f} TF | 1cta {us1:8.1f} us {fl / us1:7.1f} TF"
+              f" | cuBLAS {usb:8.1f} us {fl / usb:7.1f} TF")
 
 for mode, tag in ((1, "attn_t"), (0, "attn_s")):
     if what not in (tag, "all"):

@@ -12,8 +12,6 @@ from ctclip_b200 import _lib
 dev = torch.device("cuda")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 eng = Engine(Plan(O.init_state_dict(O.FULL, 42), Config(), dev))
-if "fuse_geglu_bwd" in sys.argv:
-    eng.fuse_geglu_bwd = True
 vol = O.synthetic_volume(O.FULL, 0, batch=B).to(dev)
 tl = eng.text_latents(O.synthetic_text_embeds(O.FULL, 7).to(dev))
 
