@@ -506,6 +506,13 @@ extern "C" int ctc_attention_set_tc_bwd(int on) {
     return prev;
 }
 
+namespace ctc { extern int g_exp2_poly; }
+extern "C" int ctc_attention_set_exp2_poly(int on) {
+    const int prev = g_exp2_poly;
+    g_exp2_poly = on ? 1 : 0;
+    return prev;
+}
+
 extern "C" int ctc_attention_score_bound(const float* q_scale, const float* k_scale, float scale,
                                          const float* bias_table, int heads, int H, int W, float* bound_dev,
                                          void* stream) {

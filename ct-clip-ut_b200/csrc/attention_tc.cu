@@ -78,6 +78,20 @@ CTC_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" :
 CTC_DEVINL uint32_t pack_bf16_rn_alu(float lo, float hi) {
     return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
+// 2^x for x in (-125, 0] on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic
+// constant, degree-4 polynomial for 2^f on [-0.5, 0.5] (relative error 4e-5, an order of magnitude below the bf16
+// rounding P receives anyway), exponent patched in with an integer add.  9 FMA/ALU-pipe instructions; used for half of
+// the exponentials of a tile so that the 16-per-clock MUFU unit and the FMA pipes share the softmax (the split FA4
+// uses on Blackwell, where d_head-sized tiles are exp-bound, not MMA-bound).
+CTC_DEVINL float exp2_poly(float x) {
+    const float t = x + 12582912.f;                       // integer part in the low mantissa bits
+    const float f = x - (t - 12582912.f);                 // [-0.5, 0.5]
+    float p = fmaf(f, 9.6181291e-3f, 5.5504109e-2f);
+    p = fmaf(f, p, 2.4022651e-1f);
+    p = fmaf(f, p, 6.9314718e-1f);
+    p = fmaf(f, p, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));    // t's low bits = n (two's complement)
+}
 CTC_DEVINL void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // normalise rows [row0, row0 + 128) of q into a SWIZZLE_64B tile; `nthreads` threads starting at `tid0` cooperate
@@ -125,6 +139,7 @@ CTC_DEVINL void tc_load_q(uint8_t* tile, const AttnParams& p, int s, int head, i
 // so the tensor core computes S(t+1) while the softmax warps work on S(t), and no warp waits on a barrier round trip.
 // The stream of key tiles runs straight through the M-tile boundaries: O is double-buffered (o_free), the next Q tile
 // is normalised by a loader warp into the other Q buffer (q_full / q_free), and there is no CTA barrier in the loop.
+template <bool POLY>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
     extern __shared__ uint8_t sm_raw[];
@@ -273,7 +288,8 @@ attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
                     for (int u = 0; u < 4; ++u) {
                         const float2 f = pair[base_i - tb[bb] - 2 * u];
                         const float p0 = fast_exp2(__uint_as_float(v[bb & 1][2 * u]) + f.x);
-                        const float p1 = fast_exp2(__uint_as_float(v[bb & 1][2 * u + 1]) + f.y);
+                        const float x1 = __uint_as_float(v[bb & 1][2 * u + 1]) + f.y;
+                        const float p1 = POLY ? exp2_poly(x1) : fast_exp2(x1);       // every other score off the MUFU pipe
                         if (u & 1) { l1 += p0; l3 += p1; } else { l0 += p0; l2 += p1; }
                         pk[bb * 4 + u] = pack_bf16(p0, p1);
                     }
@@ -610,6 +626,9 @@ __global__ void attn_score_bound_kernel(const float* __restrict__ q_scale, const
     }
 }
 
+// half of the forward softmax's exponentials on FMA-pipe polynomials (exp2_poly); ctc_attention_set_exp2_poly toggles it
+int g_exp2_poly = 1;
+
 int run_tc_bwd_dq(const AttnParams& p, cudaStream_t st) {
     const size_t nb = (size_t)(2 * p.H - 1) * (2 * p.W - 1);
     const size_t smem = 1024 + 4 * (size_t)TC_M * 64 + 3 * (size_t)p.n_pad * 64 + ((nb + 1) & ~(size_t)1) * 8 +
@@ -636,12 +655,18 @@ int run_tc_fwd(const AttnParams& p, float score_bound, cudaStream_t st) {
     
     size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            (int)cudaSharedmemCarveoutMaxShared));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             (int)cudaSharedmemCarveoutMaxShared));
         configured = smem;
     }
-    attn_tc_fwd_kernel<<<dim3(p.n_seq, p.heads), TC_THREADS, smem, st>>>(p, score_bound * LOG2E);
+    if (g_exp2_poly)
+        attn_tc_fwd_kernel<true><<<dim3(p.n_seq, p.heads), TC_THREADS, smem, st>>>(p, score_bound * LOG2E);
+    else
+        attn_tc_fwd_kernel<false><<<dim3(p.n_seq, p.heads), TC_THREADS, smem, st>>>(p, score_bound * LOG2E);
     CTC_LAUNCH_CHECK();
     return 0;
 }

@@ -51,15 +51,24 @@ layernorm_fwd_kernel(const float* __restrict__ x, int R, int C, const float* __r
 }
 
 // LayerNorm backward (input gradient only — attribution never needs weight gradients).
+// dy is read as fp32, or (dy16 != nullptr) as bf16
+CTC_DEVINL float4 load_dy4(const float* dy, const __nv_bfloat16* dy16, long long off) {
+    if (dy16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(dy16 + off);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    return *reinterpret_cast<const float4*>(dy + off);
+}
 __global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int R, int C,
-                     const float* __restrict__ gamma, float eps, float* __restrict__ out, int accumulate,
+layernorm_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ x,
+                     int R, int C, const float* __restrict__ gamma, float eps, float* __restrict__ out, int accumulate,
                      __nv_bfloat16* __restrict__ out_bf16) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= R) return;
     const float* xr = x + (long long)row * C;
-    const float* gr = dy + (long long)row * C;
+    const long long gro = (long long)row * C;
     float s = 0.f;
     for (int c = lane * 4; c < C; c += 128) {
         const float4 v = *reinterpret_cast<const float4*>(xr + c);
@@ -76,7 +85,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     float sg = 0.f, sgx = 0.f;  // sum(g), sum(g * xhat), g = dy * gamma
     for (int c = lane * 4; c < C; c += 128) {
         const float4 v = *reinterpret_cast<const float4*>(xr + c);
-        const float4 d = *reinterpret_cast<const float4*>(gr + c);
+        const float4 d = load_dy4(dy, dy16, gro + c);
         const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
         const float g0 = d.x * gm.x, g1 = d.y * gm.y, g2 = d.z * gm.z, g3 = d.w * gm.w;
         sg += (g0 + g1) + (g2 + g3);
@@ -86,7 +95,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     sgx = warp_sum(sgx) / C;
     for (int c = lane * 4; c < C; c += 128) {
         const float4 v = *reinterpret_cast<const float4*>(xr + c);
-        const float4 d = *reinterpret_cast<const float4*>(gr + c);
+        const float4 d = load_dy4(dy, dy16, gro + c);
         const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
         float4 o;
         o.x = rstd * (d.x * gm.x - sg - (v.x - mean) * rstd * sgx);
@@ -107,10 +116,10 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 // C = 512 specialisation: the row (16 floats per lane) and its gradient live in registers, so every global
 // load of a row (x, dy, the accumulate target) is issued up front and nothing is re-read.  Same summation
 // order as the generic kernel (bit-identical results).
-template <bool ACC, bool BF16OUT>
+template <bool ACC, bool BF16OUT, bool DY16>
 __global__ void __launch_bounds__(256)
-layernorm_bwd_c512_kernel(const float* __restrict__ dy, const float* __restrict__ x, int R,
-                          const float* __restrict__ gamma, float eps, float* __restrict__ out,
+layernorm_bwd_c512_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ x,
+                          int R, const float* __restrict__ gamma, float eps, float* __restrict__ out,
                           __nv_bfloat16* __restrict__ out_bf16) {
     constexpr int C = 512;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -121,7 +130,7 @@ layernorm_bwd_c512_kernel(const float* __restrict__ dy, const float* __restrict_
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         v[k] = *reinterpret_cast<const float4*>(x + base + 128 * k);
-        d[k] = *reinterpret_cast<const float4*>(dy + base + 128 * k);
+        d[k] = load_dy4(DY16 ? nullptr : dy, DY16 ? dy16 : nullptr, base + 128 * k);
         if (ACC) pr[k] = *reinterpret_cast<const float4*>(out + base + 128 * k);
         gm[k] = *reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * k);
     }
@@ -444,27 +453,41 @@ extern "C" int ctc_layernorm_fwd(const float* x, int R, int C, const float* gamm
     return 0;
 }
 
-extern "C" int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, const float* gamma, float eps,
-                                 float* out, int accumulate, void* out_bf16, void* stream) {
+static int layernorm_bwd_launch(const float* dy, const __nv_bfloat16* dy16, const float* x, int R, int C,
+                                const float* gamma, float eps, float* out, int accumulate, void* out_bf16, void* stream) {
     CTC_REQUIRE(C % 4 == 0 && R > 0, "layernorm_bwd: C=%d must be a multiple of 4, R=%d > 0", C, R);
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* ob = (__nv_bfloat16*)out_bf16;
     const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
-                      reinterpret_cast<uintptr_t>(gamma)) & 15) == 0 && (reinterpret_cast<uintptr_t>(ob) & 7) == 0;
+                      reinterpret_cast<uintptr_t>(gamma)) & 15) == 0 && (reinterpret_cast<uintptr_t>(ob) & 7) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dy16) & 7) == 0;
     if (C == 512 && al) {
         const int grid = (R + 7) / 8;
-        if (accumulate) {
-            if (ob) layernorm_bwd_c512_kernel<true, true><<<grid, 256, 0, st>>>(dy, x, R, gamma, eps, out, ob);
-            else layernorm_bwd_c512_kernel<true, false><<<grid, 256, 0, st>>>(dy, x, R, gamma, eps, out, ob);
+#define CTC_LNB(ACC, BF, D16) layernorm_bwd_c512_kernel<ACC, BF, D16><<<grid, 256, 0, st>>>(dy, dy16, x, R, gamma, eps, out, ob)
+        if (dy16) {
+            if (accumulate) { if (ob) CTC_LNB(true, true, true); else CTC_LNB(true, false, true); }
+            else { if (ob) CTC_LNB(false, true, true); else CTC_LNB(false, false, true); }
         } else {
-            if (ob) layernorm_bwd_c512_kernel<false, true><<<grid, 256, 0, st>>>(dy, x, R, gamma, eps, out, ob);
-            else layernorm_bwd_c512_kernel<false, false><<<grid, 256, 0, st>>>(dy, x, R, gamma, eps, out, ob);
+            if (accumulate) { if (ob) CTC_LNB(true, true, false); else CTC_LNB(true, false, false); }
+            else { if (ob) CTC_LNB(false, true, false); else CTC_LNB(false, false, false); }
         }
+#undef CTC_LNB
     } else {
-        layernorm_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(dy, x, R, C, gamma, eps, out, accumulate, ob);
+        layernorm_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(dy, dy16, x, R, C, gamma, eps, out, accumulate, ob);
     }
     CTC_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, const float* gamma, float eps,
+                                 float* out, int accumulate, void* out_bf16, void* stream) {
+    return layernorm_bwd_launch(dy, nullptr, x, R, C, gamma, eps, out, accumulate, out_bf16, stream);
+}
+
+extern "C" int ctc_layernorm_bwd_bf16(const void* dy_bf16, const float* x, int R, int C, const float* gamma, float eps,
+                                      float* out, int accumulate, void* out_bf16, void* stream) {
+    CTC_REQUIRE(dy_bf16 != nullptr && C % 4 == 0, "layernorm_bwd_bf16: dy missing or C=%d not a multiple of 4", C);
+    return layernorm_bwd_launch(nullptr, (const __nv_bfloat16*)dy_bf16, x, R, C, gamma, eps, out, accumulate, out_bf16, stream);
 }
 
 extern "C" int ctc_peg(const float* x, int B, int T, int H, int W, int C, const float* w27, const float* bias,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "ctc_patchify_ln_bwd": [P, L, I, I, I, I, I, I, P, F, P, P, P, I, F, P],
     "ctc_layernorm_fwd": [P, I, I, P, P, F, P, P, P, P],
     "ctc_layernorm_bwd": [P, P, I, I, P, F, P, I, P, P],
+    "ctc_layernorm_bwd_bf16": [P, P, I, I, P, F, P, I, P, P],
     "ctc_peg": [P, I, I, I, I, I, P, P, I, I, P, P, P],
     "ctc_peg_frames": [P, P, P, I, I, I, I, P, P, P, P],
     "ctc_frames_gather": [P, P, P, I, L, P, P],
@@ -72,7 +73,7 @@ SIGNATURES = {
 }
 OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, []),
                  "ctc_launch_count": (ctypes.c_longlong, []), "ctc_vq_num_candidates": (c_int, [c_int]),
-                 "ctc_attention_set_tc_bwd": (c_int, [c_int]), "ctc_colmean_ws_floats": (c_int, [c_int, c_int]),
+                 "ctc_attention_set_tc_bwd": (c_int, [c_int]), "ctc_attention_set_exp2_poly": (c_int, [c_int]), "ctc_colmean_ws_floats": (c_int, [c_int, c_int]),
                  "ctc_kth_value_ws_bytes": (c_int, [])}
 
 EPI_BF16, EPI_F32, EPI_ARGMAX, EPI_GEGLU, EPI_GEGLU_BWD = 0, 1, 2, 3, 4

@@ -159,8 +159,10 @@ class Engine:
         call("ctc_layernorm_fwd", x, R, C, g, b, LN_EPS, y_bf16, y_f32, xraw, stream_ptr())
 
     def layernorm_bwd(self, dy, x, g, out, accumulate, out_bf16=None):
+        """dy fp32 or bf16 (the GEMM that produced it wrote bf16: half the bytes of this HBM-bound pass)"""
         R, C = x.shape
-        call("ctc_layernorm_bwd", dy, x, R, C, g, LN_EPS, out, int(accumulate), out_bf16, stream_ptr())
+        name = "ctc_layernorm_bwd_bf16" if dy.dtype == torch.bfloat16 else "ctc_layernorm_bwd"
+        call(name, dy, x, R, C, g, LN_EPS, out, int(accumulate), out_bf16, stream_ptr())
 
     # ------------------------------------------------------------------ text tower tail
     def text_latents(self, text_embeds: torch.Tensor) -> torch.Tensor:
@@ -409,7 +411,7 @@ class Engine:
             dh = self.gemm(dx3_bf, lw.w2_t, self._empty(R, FP, dtype=bf), EPI_BF16)
             call("ctc_geglu_bwd", lc.u, dh, R, FP, du, stream_ptr())
             del dh
-        dxn2 = self.gemm(du, lw.w1_t, self._empty(R, C), EPI_F32)
+        dxn2 = self.gemm(du, lw.w1_t, self._empty(R, C, dtype=bf), EPI_BF16)     # consumed once, by the LN adjoint
         del du
         dx2, dx2_bf = dx3, dx3_bf
         self.layernorm_bwd(dxn2, lc.x2, lw.ff_ln_w, dx2, True, dx2_bf)
@@ -425,10 +427,10 @@ class Engine:
              self.plan.bias_table if mode == MODE_SPATIAL else None, mode, dq, inner, dkv,
              dkv.data_ptr() + inner * 2, 2 * inner, delta, stream_ptr())
         dx1 = self.gemm(dkv, lw.wkv_t, dx2, EPI_F32, resid=dx2)           # k/v read the raw stream
-        dxn = self.gemm(dq, lw.wq_t, dxn2, EPI_F32)
+        dxn = self.gemm(dq, lw.wq_t, dxn2, EPI_BF16)
         self.layernorm_bwd(dxn, lc.x1, lw.ln_g, dx1, True, None)
         # ---- PEG adjoint
-        dx0, dx0_bf = dxn, dx2_bf
+        dx0, dx0_bf = self._empty(R, C), dx2_bf
         call("ctc_peg", dx1, B, T, H, W, C, lw.w27, None, mode, 1, dx0, dx0_bf, stream_ptr())
         return dx0, dx0_bf
 

@@ -79,6 +79,9 @@ int ctc_layernorm_fwd(const float* x, int R, int C, const float* gamma, const fl
 /* dx = LN'(x)·(dy*gamma); out[r] = (accumulate ? out[r] : 0) + dx; optional bf16 copy of out. */
 int ctc_layernorm_bwd(const float* dy, const float* x, int R, int C, const float* gamma, float eps, float* out,
                       int accumulate, void* out_bf16, void* stream);
+/* The same with the incoming gradient in bf16 (as a GEMM's bf16 epilogue leaves it: half the bytes of the pass). */
+int ctc_layernorm_bwd_bf16(const void* dy_bf16, const float* x, int R, int C, const float* gamma, float eps, float* out,
+                           int accumulate, void* out_bf16, void* stream);
 
 /* PEG (attention.py:55-83): y = x + dwconv3d(pad(x)) + bias, causal padding (2,0) on the first
  * grid axis.  mode TEMPORAL reproduces the reference's axis scramble: the flat
@@ -117,6 +120,9 @@ int ctc_attention_fwd(const void* q, int64_t ldq, const void* k, const void* v, 
 int ctc_attention_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int B, int T, int H,
                          int W, int heads, const float* q_scale, const float* k_scale, float scale,
                          const float* bias_table, float score_bound, void* o, float* lse, void* stream);
+/* Spatial forward kernel: compute every other exponential of the softmax with an FMA-pipe polynomial instead of
+ * MUFU.EX2 (default on; returns the previous setting).  A/B measurement switch. */
+int ctc_attention_set_exp2_poly(int on);
 /* Opt-in: compute dQ of the spatial backward on tcgen05 / TMEM as well (same result to bf16 rounding; measured
  * 4 % slower than the mma.sync kernel, so off by default).  Returns the previous setting (NOT a status code). */
 int ctc_attention_set_tc_bwd(int on);

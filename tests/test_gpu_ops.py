@@ -104,6 +104,14 @@ def test_layernorm_fwd_bwd(lib, R, C):
     assert relerr(o16, dx_ref + prev) < 1e-2
     lib.call("ctc_layernorm_bwd", dy, x, R, C, g, 1e-5, out, 0, None, lib.stream_ptr())
     assert relerr(out, dx_ref) < 1e-5
+    # incoming gradient in bf16 (what the dgrad GEMMs' bf16 epilogue hands over): exact w.r.t. the rounded dy
+    dy16 = dy.to(torch.bfloat16)
+    (dx_ref16,) = torch.autograd.grad(F.layer_norm(xr, (C,), g, b), xr, dy16.float())
+    out = prev.clone()
+    lib.call("ctc_layernorm_bwd_bf16", dy16, x, R, C, g, 1e-5, out, 1, o16, lib.stream_ptr())
+    assert relerr(out, dx_ref16 + prev) < 1e-5
+    lib.call("ctc_layernorm_bwd_bf16", dy16, x, R, C, g, 1e-5, out, 0, None, lib.stream_ptr())
+    assert relerr(out, dx_ref16) < 1e-5
 
 
 # --------------------------------------------------------------------------------------- PEG

@@ -77,4 +77,10 @@ for mode, tag in ((1, "attn_t"), (0, "attn_s")):
         def fwd_tc():
             L.call("ctc_attention_fwd_tc", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, B, T, H, W, heads, qs, ks,
                    8.0, table, bound, o, lse, L.stream_ptr())
-        print(f"  {tag} fwd tcgen05 {timeit(fwd_tc):8.1f} us (score bound {bound:.2f})")
+        lib = L.load()
+        lib.ctc_attention_set_exp2_poly(0)
+        t_mufu = timeit(fwd_tc)
+        lib.ctc_attention_set_exp2_poly(1)
+        t_poly = timeit(fwd_tc)
+        print(f"  {tag} fwd tcgen05: all exponentials on MUFU {t_mufu:8.1f} us | half on FMA-pipe polynomials {t_poly:8.1f} us "
+              f"(score bound {bound:.2f})")
