@@ -470,7 +470,7 @@ static int run_fwd(AttnParams& p, cudaStream_t st) {
 // (ctc_attention_set_tc_bwd) and the mma.sync kernel stays the default.
 static int g_tc_bwd = 0;
 static bool tc_bwd_eligible(const AttnParams& p) {
-    return g_tc_bwd && p.bias_table != nullptr && p.mode == CTC_MODE_SPATIAL && p.n % 64 == 0 && p.W % 8 == 0 && p.n >= 64 &&
+    return g_tc_bwd == 1 && p.bias_table != nullptr && p.mode == CTC_MODE_SPATIAL && p.n % 64 == 0 && p.W % 8 == 0 && p.n >= 64 &&
            (size_t)p.n * 192 + 60 * 1024 <= 220 * 1024;
 }
 
@@ -482,6 +482,8 @@ static int run_bwd(AttnParams& p, cudaStream_t st) {
     const size_t smem_dkv = (size_t)HPC * (p.n_pad * 128 + 2 * QB * 64 + 2 * p.n_pad * 4) + 256 + p.n_pad * 4 + nb * 8;
     const int threads = HPC * (QB / 16) * 32;
     if constexpr (HPC == 1 && KBLK == 64) {
+        // g_tc_bwd == 2: dQ, dK and dV in one pass on tcgen05 / TMEM (attention_tc_bwd.cu)
+        if (g_tc_bwd == 2 && tc_bwd_onepass_eligible(p)) return run_tc_bwd_onepass(p, st);
         if (fast_bias(p)) {
             if (tc_bwd_eligible(p)) {           // dQ (and D = rowsum(dO o O)) on tcgen05 / TMEM
                 if (int e = run_tc_bwd_dq(p, st)) return e;
@@ -500,9 +502,9 @@ static int run_bwd(AttnParams& p, cudaStream_t st) {
 
 using namespace ctc;
 
-extern "C" int ctc_attention_set_tc_bwd(int on) {
+extern "C" int ctc_attention_set_tc_bwd(int mode) {
     const int prev = g_tc_bwd;
-    g_tc_bwd = on ? 1 : 0;
+    g_tc_bwd = (mode == 1 || mode == 2) ? mode : 0;
     return prev;
 }
 

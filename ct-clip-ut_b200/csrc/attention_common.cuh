@@ -256,6 +256,9 @@ int run_small_bwd(const AttnParams& p, cudaStream_t st);
 // attention_tc.cu
 int run_tc_fwd(const AttnParams& p, float score_bound, cudaStream_t st);
 int run_tc_bwd_dq(const AttnParams& p, cudaStream_t st);
+// attention_tc_bwd.cu
+bool tc_bwd_onepass_eligible(const AttnParams& p);
+int run_tc_bwd_onepass(const AttnParams& p, cudaStream_t st);
 int attn_score_bound(const float* q_scale, const float* k_scale, float scale, const float* bias_table, int n_bias,
                      float* out, cudaStream_t st);
 

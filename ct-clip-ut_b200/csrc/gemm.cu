@@ -217,6 +217,24 @@ CTC_DEVINL void stage_load_bf16_64(const GemmArgs& g, uint8_t* stage, int row0, 
     __syncwarp();
 }
 
+// the same load split in two halves, so that the global loads of the NEXT chunk are in flight (in registers) while the
+// current chunk is processed: issue (global -> registers) ... later ... commit (registers -> swizzled staging tile)
+CTC_DEVINL void stage_load_issue(const GemmArgs& g, int row0, int col0, int lane, const __nv_bfloat16* src, long long ld,
+                                 uint4 (&reg)[8]) {
+    const int u = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = row0 + (lane >> 3) + 4 * i;
+        reg[i] = (row < g.M) ? *reinterpret_cast<const uint4*>(src + (long long)row * ld + col0 + u * 8) : make_uint4(0, 0, 0, 0);
+    }
+}
+CTC_DEVINL void stage_load_commit(uint8_t* stage, int lane, const uint4 (&reg)[8]) {
+    const int u = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stage + stage_off((lane >> 3) + 4 * i, u)) = reg[i];
+    __syncwarp();
+}
+
 // running top-2 (value, column) over a row, used by the VQ nearest-code search
 struct Top2 {
     float v0, v1;
@@ -372,6 +390,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         if (pcol + c < 2 * g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + c));
                 }
             }
+            uint4 ureg[EPI == CTC_EPI_GEGLU_BWD ? 8 : 1];
+            if constexpr (EPI == CTC_EPI_GEGLU_BWD) {
+                // first chunk of the saved adjoint factors: in registers before the accumulator is even complete
+                if (tn * BN + cbeg < g.N)
+                    stage_load_issue(g, rbase + ew * 32, 2 * (tn * BN + cbeg), lane,
+                                     reinterpret_cast<const __nv_bfloat16*>(g.aux), g.ldaux, ureg);
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int row = rbase + ew * 32 + lane;
@@ -465,15 +490,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int c = cbeg; c < cend; c += 32) {
                     const int col0 = tn * BN + c;
                     if (col0 >= g.N) break;
-                    stage_load_bf16_64(g, stage, row0, 2 * col0, lane, uin, g.ldaux);
+                    stage_load_commit(stage, lane, ureg);
                     uint32_t dh[32];
                     tmem_ld_32x32b_x32(taddr + c, dh);
+                    uint4 aa4[4], ba4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        aa4[u] = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u));
+                        ba4[u] = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u + 4));
+                    }
+                    // next chunk's factors on their way while this one is multiplied and stored
+                    if (c + 32 < cend && col0 + 32 < g.N) stage_load_issue(g, row0, 2 * (col0 + 32), lane, uin, g.ldaux, ureg);
                     tmem_ld_wait();
                     uint32_t pk[32];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const uint4 aa = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u));
-                        const uint4 ba = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u + 4));
+                        const uint4 aa = aa4[u];
+                        const uint4 ba = ba4[u];
                         const uint32_t as[4] = {aa.x, aa.y, aa.z, aa.w}, bs[4] = {ba.x, ba.y, ba.z, ba.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -691,7 +724,12 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
     // CTA pairs (cta_group::2, 256 x 256 tiles) for every 256-wide case unless the caller asks for the single-CTA kernel
     // (CTC_GEMM_PAIR=0 in the environment switches the default back to single CTAs: an A/B measurement aid)
     static const int pair_env = [] { const char* e = getenv("CTC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
-    const bool pair = bn256 && impl != CTC_GEMM_TCGEN05_1CTA && pair_env && (num_sms() % 2 == 0);
+    // Measured on B200 at M = 110 592 (tools/kernel_bench.py, profiles/r02_gemm_pair_vs_1cta.md): pairs win 3-10 % where both
+    // the reduction and the output are wide (to_kv, FF2, dh, dxn2, patch embedding and its adjoint) and lose 3-6 % on the
+    // narrow to_q / to_out launches and under the arithmetic-heavy GEGLU epilogue, where the leader's MMA issue has to
+    // wait for the slower of two epilogues; impl = CTC_GEMM_TCGEN05_PAIR forces pairs everywhere (tests).
+    const bool want_pair = impl == CTC_GEMM_TCGEN05_PAIR || (pair_env && K >= 512 && N >= 512 && epi != CTC_EPI_GEGLU);
+    const bool pair = bn256 && impl != CTC_GEMM_TCGEN05_1CTA && want_pair && (num_sms() % 2 == 0);
     g.n_tiles_n = (N + BNsel - 1) / BNsel;
     CUtensorMap ta, tb;
     if (int e = make_tmap_bf16(&ta, A, M, K, lda, BM)) return e;

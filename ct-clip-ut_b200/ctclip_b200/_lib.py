@@ -77,7 +77,7 @@ OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, []),
                  "ctc_kth_value_ws_bytes": (c_int, [])}
 
 EPI_BF16, EPI_F32, EPI_ARGMAX, EPI_GEGLU, EPI_GEGLU_BWD = 0, 1, 2, 3, 4
-GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_1CTA = 0, 1, 2
+GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_1CTA, GEMM_TCGEN05_PAIR = 0, 1, 2, 3
 MODE_SPATIAL, MODE_TEMPORAL = 0, 1
 
 _lib = None

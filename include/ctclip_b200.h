@@ -30,9 +30,10 @@ extern "C" {
 
 /* GEMM epilogues */
 enum { CTC_EPI_BF16 = 0, CTC_EPI_F32 = 1, CTC_EPI_ARGMAX = 2, CTC_EPI_GEGLU = 3, CTC_EPI_GEGLU_BWD = 4 };
-/* GEMM implementation: tcgen05 is the product path (CTA pairs / cta_group::2 wherever the tile is 256 wide);
- * TCGEN05_1CTA forces the single-CTA (cta_group::1) kernel and SIMT is a plain comparator - both for tests. */
-enum { CTC_GEMM_TCGEN05 = 0, CTC_GEMM_SIMT = 1, CTC_GEMM_TCGEN05_1CTA = 2 };
+/* GEMM implementation: tcgen05 is the product path (CTA pairs / cta_group::2 for the shapes where they measure
+ * faster, single CTAs otherwise); TCGEN05_1CTA / TCGEN05_PAIR force one kernel and SIMT is a plain comparator -
+ * all three for tests and A/B measurements. */
+enum { CTC_GEMM_TCGEN05 = 0, CTC_GEMM_SIMT = 1, CTC_GEMM_TCGEN05_1CTA = 2, CTC_GEMM_TCGEN05_PAIR = 3 };
 /* sequence mode of the factorised transformer (ctvit.py:94-101) */
 enum { CTC_MODE_SPATIAL = 0, CTC_MODE_TEMPORAL = 1 };
 

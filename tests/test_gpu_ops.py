@@ -34,7 +34,7 @@ def relerr(a, b):
 
 
 # --------------------------------------------------------------------------------------- GEMM
-@pytest.mark.parametrize("impl", [0, 1, 2])        # 0 = tcgen05 CTA pairs (product), 1 = SIMT, 2 = tcgen05 single CTA
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])     # 0 = tcgen05 product path, 1 = SIMT, 2 = single CTAs, 3 = CTA pairs
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 200, 136), (1000, 512, 512), (2048, 1408, 512),
                                    (13824, 512, 4000), (4096, 256, 512), (1536, 2816, 512), (512, 4000, 512),
                                    (777, 64, 256), (256, 512, 2816), (129, 256, 512), (38016, 512, 512)])
@@ -49,7 +49,7 @@ def test_gemm_bf16_out(lib, impl, M, N, K):
     assert relerr(out, ref) < 1e-2
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])        # 0 = tcgen05 CTA pairs (product), 1 = SIMT, 2 = tcgen05 single CTA
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])     # 0 = tcgen05 product path, 1 = SIMT, 2 = single CTAs, 3 = CTA pairs
 @pytest.mark.parametrize("M,N,K", [(256, 512, 256), (999, 512, 1408), (13824, 512, 256), (130, 64, 256), (300, 256, 512), (4161, 1408, 512)])
 def test_gemm_f32_bias_resid(lib, impl, M, N, K):
     a = rnd(M, K, seed=3, dtype=torch.bfloat16)
@@ -240,6 +240,19 @@ def test_attention_bwd_dq_on_tcgen05(lib, B, T, H, W, heads):
         lib.load().ctc_attention_set_tc_bwd(prev)
 
 
+@pytest.mark.parametrize("B,T,H,W,heads", [(1, 2, 24, 24, 8), (1, 3, 8, 8, 2), (2, 1, 16, 8, 1), (1, 1, 16, 24, 3)])
+def test_attention_bwd_one_pass_on_tcgen05(lib, B, T, H, W, heads):
+    """dQ, dK and dV from ONE recomputation of the probabilities on tcgen05 / TMEM (attention_tc_bwd.cu), against the
+    same torch fp32 reference as the two-kernel mma.sync path; twice, and bit-identical (no atomics)."""
+    prev = lib.load().ctc_attention_set_tc_bwd(2)
+    try:
+        a = _attention_fwd_bwd_probs(lib, 0, B, T, H, W, heads)
+        b = _attention_fwd_bwd_probs(lib, 0, B, T, H, W, heads)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    finally:
+        lib.load().ctc_attention_set_tc_bwd(prev)
+
+
 def _attention_fwd_bwd_probs(lib, mode, B, T, H, W, heads):
     if mode == 1 and not (T == H == W):
         pytest.skip("temporal mode uses T tokens")
@@ -284,6 +297,7 @@ def _attention_fwd_bwd_probs(lib, mode, B, T, H, W, heads):
     assert relerr(dq, dq_ref) < 4e-2
     assert relerr(dkv[:, :inner], dkv_ref[:, :inner]) < 4e-2
     assert relerr(dkv[:, inner:], dkv_ref[:, inner:]) < 4e-2
+    return dq, dkv
 
 
 @pytest.mark.parametrize("B,T,H,W,heads", [(1, 2, 24, 24, 8), (1, 3, 8, 8, 2), (2, 1, 16, 8, 1), (1, 1, 16, 16, 2)])
@@ -360,9 +374,10 @@ def test_gemm_fused_geglu_epilogues(lib, M, Fp, K):
     (dgelu,) = torch.autograd.grad(F.gelu(xg_).sum(), xg_)
     assert relerr(u, _group(F.gelu(xg), xv * dgelu)) < 1e-2
     assert relerr(h, F.gelu(xg) * xv) < 1e-2
-    h1, u1 = torch.empty_like(h), torch.empty_like(u)          # single-CTA kernel: same accumulation order, same bits
-    lib.call("ctc_gemm_bf16", a, K, w, K, h1, Fp, M, 2 * Fp, K, lib.EPI_GEGLU, None, None, 0, u1, 2 * Fp, 2, lib.stream_ptr())
-    assert torch.equal(h, h1) and torch.equal(u, u1)
+    for impl in (2, 3):                                        # single CTAs / CTA pairs: same accumulation order, same bits
+        h1, u1 = torch.empty_like(h), torch.empty_like(u)
+        lib.call("ctc_gemm_bf16", a, K, w, K, h1, Fp, M, 2 * Fp, K, lib.EPI_GEGLU, None, None, 0, u1, 2 * Fp, impl, lib.stream_ptr())
+        assert torch.equal(h, h1) and torch.equal(u, u1)
     h2 = torch.empty_like(h)                                   # without the pre-activation output
     lib.call("ctc_gemm_bf16", a, K, w, K, h2, Fp, M, 2 * Fp, K, lib.EPI_GEGLU, None, None, 0, None, 0, 0, lib.stream_ptr())
     assert torch.equal(h, h2)
@@ -373,6 +388,11 @@ def test_gemm_fused_geglu_epilogues(lib, M, Fp, K):
     du = torch.full((M, 2 * Fp), float("nan"), device=dev(), dtype=torch.bfloat16)
     lib.call("ctc_gemm_bf16", d, Kd, w2t, Kd, du, 2 * Fp, M, Fp, Kd, lib.EPI_GEGLU_BWD, None, None, 0, u, 2 * Fp, 0,
              lib.stream_ptr())
+    for impl in (2, 3):
+        du1 = torch.full_like(du, float("nan"))
+        lib.call("ctc_gemm_bf16", d, Kd, w2t, Kd, du1, 2 * Fp, M, Fp, Kd, lib.EPI_GEGLU_BWD, None, None, 0, u, 2 * Fp, impl,
+                 lib.stream_ptr())
+        assert torch.equal(du, du1)
     dh = d.float() @ w2t.float().t()
     xs, gs = xv.clone().requires_grad_(), xg.clone().requires_grad_()
     dx_ref, dg_ref = torch.autograd.grad(F.gelu(gs) * xs, [xs, gs], dh)

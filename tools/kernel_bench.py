@@ -32,20 +32,24 @@ def rnd(*shape, dtype=torch.float32, scale=1.0):
 if what in ("gemm", "all"):
     for name, N, K, epi, resid in [("q", 256, 512, L.EPI_BF16, False), ("kv", 512, 512, L.EPI_BF16, False),
                                    ("out+res", 512, 256, L.EPI_F32, True), ("ff1 geglu (no u)", 2816, 512, L.EPI_GEGLU, False),
-                                   ("ff2+res", 512, 1408, L.EPI_F32, True), ("dh", 1408, 512, L.EPI_BF16, False),
+                                   ("ff2+res", 512, 1408, L.EPI_F32, True), ("dh", 1408, 512, L.EPI_BF16, False), ("dh + geglu adjoint", 1408, 512, L.EPI_GEGLU_BWD, False),
                                    ("dxn2", 512, 2816, L.EPI_F32, False), ("pe", 512, 4000, L.EPI_F32, False),
                                    ("pe bwd", 4000, 512, L.EPI_BF16, False)]:
         a = rnd(R, K, dtype=bf)
         w = rnd(N, K, dtype=bf, scale=K ** -0.5)
-        if epi == L.EPI_GEGLU:
+        aux = None
+        if epi == L.EPI_GEGLU_BWD:
+            out = torch.empty(R, 2 * N, device=dev, dtype=bf)
+            aux = rnd(R, 2 * N, dtype=bf)
+        elif epi == L.EPI_GEGLU:
             out = torch.empty(R, N // 2, device=dev, dtype=bf)
         else:
             out = torch.empty(R, N, device=dev, dtype=bf if epi == L.EPI_BF16 else torch.float32)
         res = rnd(R, N) if resid else None
         def f(impl=0):
-            L.call("ctc_gemm_bf16", a, K, w, K, out, out.stride(0), R, N, K, epi, None, res, N if resid else 0, None, 0, impl,
-                   L.stream_ptr())
-        us = timeit(f)                       # CTA pairs (cta_group::2), the product path
+            L.call("ctc_gemm_bf16", a, K, w, K, out, out.stride(0), R, N, K, epi, None, res, N if resid else 0, aux,
+                   aux.stride(0) if aux is not None else 0, impl, L.stream_ptr())
+        us = timeit(lambda: f(3))            # CTA pairs (cta_group::2)
         us1 = timeit(lambda: f(2))           # single-CTA kernel (cta_group::1)
         usb = timeit(lambda: torch.matmul(a, w.t()))     # cuBLAS, bare bf16 GEMM (no epilogue work)
         fl = 2.0 * R * N * K / 1e6
@@ -69,7 +73,17 @@ for mode, tag in ((1, "attn_t"), (0, "attn_s")):
     def bwd():
         L.call("ctc_attention_bwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, o, d_o, lse, B, T, H, W, heads,
                qs, ks, 8.0, table, mode, dq, inner, dkv, dkv.data_ptr() + inner * 2, 2 * inner, delta, L.stream_ptr())
-    print(f"  {tag} fwd {timeit(fwd):8.1f} us   bwd (dq + dkv) {timeit(bwd):8.1f} us")
+    print(f"  {tag} fwd {timeit(fwd):8.1f} us   bwd (dq + dkv, mma.sync) {timeit(bwd):8.1f} us")
+    if mode == 0:
+        lib = L.load()
+        lib.ctc_attention_set_tc_bwd(2)
+        t1 = timeit(bwd)
+        ref = (dq.clone(), dkv.clone())
+        lib.ctc_attention_set_tc_bwd(0)
+        bwd(); torch.cuda.synchronize()
+        err = max(float((dq.float() - ref[0].float()).abs().max() / dq.float().abs().max()),
+                  float((dkv.float() - ref[1].float()).abs().max() / dkv.float().abs().max()))
+        print(f"  {tag} bwd one pass on tcgen05 (dq, dk, dv) {t1:8.1f} us   (max rel diff to the mma.sync kernels {err:.2e})")
     if mode == 0:
         bt = torch.empty(1, device=dev)
         L.call("ctc_attention_score_bound", qs, ks, 8.0, table, heads, H, W, bt, L.stream_ptr())
