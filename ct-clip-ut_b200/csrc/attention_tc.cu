@@ -519,8 +519,11 @@ __global__ void attn_score_bound_kernel(const float* __restrict__ q_scale, const
     }
 }
 
-// half of the forward softmax's exponentials on FMA-pipe polynomials (exp2_poly); ctc_attention_set_exp2_poly toggles it
-int g_exp2_poly = 1;
+// half of the forward softmax's exponentials on FMA-pipe polynomials (exp2_poly); ctc_attention_set_exp2_poly toggles it.
+// OFF by default: measured on B200 at batch 8 (tools/kernel_bench.py attn_s, profiles/r02_kernel_bench.md) the split
+// runs 388 us against 320 us with every exponential on MUFU - the kernel is issue-bound (9 FMA/ALU-pipe instructions
+// replace one MUFU op in warps that already saturate their schedulers), not MUFU-bound.
+int g_exp2_poly = 0;
 
 int run_tc_bwd_dq(const AttnParams& p, cudaStream_t st) {
     const size_t nb = (size_t)(2 * p.H - 1) * (2 * p.W - 1);

@@ -138,8 +138,8 @@ static constexpr int LAT_CH = 1024;
 static constexpr int LAT_BMAX = 8;
 
 __global__ void __launch_bounds__(256)
-latent_proj_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __restrict__ wv, int B, long long L, int NL,
-                   float* __restrict__ partial) {
+latent_proj_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __restrict__ wv,
+                   const __nv_bfloat16* __restrict__ wv_lo, int B, long long L, int NL, float* __restrict__ partial) {
     __shared__ float sp[LAT_BMAX][LAT_CH];
     const int chunk = blockIdx.x;
     const int b0 = blockIdx.y * LAT_BMAX;
@@ -163,6 +163,12 @@ latent_proj_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __rest
             float wf[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) { const float2 t = unpack_bf16(ww[e]); wf[2 * e] = t.x; wf[2 * e + 1] = t.y; }
+            if (wv_lo) {                                              // W = hi + lo (both bf16): ~16 mantissa bits
+                const uint4 l4 = *reinterpret_cast<const uint4*>(wv_lo + (long long)n * L + l0 + l);
+                const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 t = unpack_bf16(lw[e]); wf[2 * e] += t.x; wf[2 * e + 1] += t.y; }
+            }
 #pragma unroll
             for (int b = 0; b < LAT_BMAX; ++b) {
                 const float4 p0 = *reinterpret_cast<const float4*>(&sp[b][l]);
@@ -184,12 +190,16 @@ latent_proj_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __rest
 // weight chunk from HBM ONCE for up to 32 batch rows with mma.sync m16n8k16: the reduction index inside a 32-wide
 // k-block is permuted (thread t owns k = 8t .. 8t+7 of both operands), so that the weight fragment is ONE 16-byte
 // global load per lane and the pooled fragment two float4 loads - no shared memory, no ldmatrix.  The fp32 pooled
-// row is split into bf16 hi + lo parts (two MMAs), which keeps ~16 mantissa bits of the activations; the weights
-// are bf16 as before.  Partials go to partial[chunk, b, n] and are reduced by latent_reduce_kernel (deterministic).
-template <int MT>
+// row is split into bf16 hi + lo parts (two MMAs), which keeps ~16 mantissa bits of the activations.  The WEIGHT is
+// split the same way when wv_lo is given (W = hi + lo, lo = bf16(W - hi); a third MMA, hi-activation x lo-weight):
+// this 294 912-long dot product decides a logit of magnitude 1e-2 whose DIFFERENCES between occluded volumes are the
+// attribution signal, and the 2^-9 rounding of a bf16-only weight showed up as a 4e-4 logit error with every VQ code
+// identical to the reference (profiles/r02_parity.md) - the projection is 0.04 % of the FLOPs and HBM-bound either
+// way.  Partials go to partial[chunk, b, n] and are reduced by latent_reduce_kernel (deterministic).
+template <int MT, bool LO>
 __global__ void __launch_bounds__(256, 1)
-latent_proj_mma_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __restrict__ wv, int B, long long L, int NL,
-                       float* __restrict__ partial) {
+latent_proj_mma_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __restrict__ wv,
+                       const __nv_bfloat16* __restrict__ wv_lo, int B, long long L, int NL, float* __restrict__ partial) {
     const int chunk = blockIdx.x;
     const int b0 = blockIdx.y * (16 * MT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,10 +216,13 @@ latent_proj_mma_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __
             for (int i = 0; i < 8; ++i) acc[m][i][0] = acc[m][i][1] = acc[m][i][2] = acc[m][i][3] = 0.f;
         for (int kb = 0; kb < len; kb += 32) {
             // weight fragments of the 8 n-tiles: 8 independent 16-byte loads in flight per lane
-            uint4 wf[8];
+            uint4 wf[8], wl[LO ? 8 : 1];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 8; ++i) {
                 wf[i] = *reinterpret_cast<const uint4*>(wv + (long long)(n_w + 8 * i + g) * L + l0 + kb + 8 * t);
+                if constexpr (LO)
+                    wl[i] = *reinterpret_cast<const uint4*>(wv_lo + (long long)(n_w + 8 * i + g) * L + l0 + kb + 8 * t);
+            }
             // pooled fragments (rows g, g+8 of each m-tile), split into bf16 hi / lo
             uint32_t ah[MT][2][4], al[MT][2][4];                      // [m-tile][k-step j][a0..a3]
 #pragma unroll
@@ -246,6 +259,13 @@ latent_proj_mma_kernel(const float* __restrict__ pooled, const __nv_bfloat16* __
                         mma_bf16_16816(acc[m][i], ah[m][j], wr[2 * j], wr[2 * j + 1]);
                         mma_bf16_16816(acc[m][i], al[m][j], wr[2 * j], wr[2 * j + 1]);
                     }
+                if constexpr (LO) {
+                    const uint32_t lr[4] = {wl[i].x, wl[i].y, wl[i].z, wl[i].w};
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) mma_bf16_16816(acc[m][i], ah[m][j], lr[2 * j], lr[2 * j + 1]);
+                }
             }
         }
 #pragma unroll
@@ -444,22 +464,27 @@ extern "C" int ctc_vq_bwd(const float* dpooled, const float* dtokens, const floa
     return 0;
 }
 
-extern "C" int ctc_latent_proj(const float* pooled, const void* wv_bf16, int B, int64_t L, int NL, float* partial,
-                               int n_chunks, float* latent, void* stream) {
+extern "C" int ctc_latent_proj(const float* pooled, const void* wv_bf16, const void* wv_lo_bf16, int B, int64_t L, int NL,
+                               float* partial, int n_chunks, float* latent, void* stream) {
     const int need = (int)((L + LAT_CH - 1) / LAT_CH);
     CTC_REQUIRE(n_chunks == need, "latent_proj: partial buffer must have %d chunks (got %d)", need, n_chunks);
     CTC_REQUIRE(L % 8 == 0, "latent_proj: L=%lld must be a multiple of 8", (long long)L);
     const bool mma_ok = NL % 64 == 0 && L % 64 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(wv_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial) & 7) == 0;
+                        (reinterpret_cast<uintptr_t>(wv_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial) & 7) == 0 &&
+                        (reinterpret_cast<uintptr_t>(wv_lo_bf16) & 15) == 0;
+    const __nv_bfloat16* wh = (const __nv_bfloat16*)wv_bf16;
+    const __nv_bfloat16* wlo = (const __nv_bfloat16*)wv_lo_bf16;
+    cudaStream_t st = (cudaStream_t)stream;
     if (mma_ok && B > 16) {
-        latent_proj_mma_kernel<2><<<dim3(n_chunks, (B + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
-            pooled, (const __nv_bfloat16*)wv_bf16, B, L, NL, partial);
+        const dim3 grid(n_chunks, (B + 31) / 32);
+        if (wlo) latent_proj_mma_kernel<2, true><<<grid, 256, 0, st>>>(pooled, wh, wlo, B, L, NL, partial);
+        else latent_proj_mma_kernel<2, false><<<grid, 256, 0, st>>>(pooled, wh, wlo, B, L, NL, partial);
     } else if (mma_ok) {
-        latent_proj_mma_kernel<1><<<dim3(n_chunks, 1), 256, 0, (cudaStream_t)stream>>>(
-            pooled, (const __nv_bfloat16*)wv_bf16, B, L, NL, partial);
+        if (wlo) latent_proj_mma_kernel<1, true><<<dim3(n_chunks, 1), 256, 0, st>>>(pooled, wh, wlo, B, L, NL, partial);
+        else latent_proj_mma_kernel<1, false><<<dim3(n_chunks, 1), 256, 0, st>>>(pooled, wh, wlo, B, L, NL, partial);
     } else {
         dim3 grid(n_chunks, (B + LAT_BMAX - 1) / LAT_BMAX);
-        latent_proj_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pooled, (const __nv_bfloat16*)wv_bf16, B, L, NL, partial);
+        latent_proj_kernel<<<grid, 256, 0, st>>>(pooled, wh, wlo, B, L, NL, partial);
     }
     CTC_LAUNCH_CHECK();
     const int total = B * NL;

@@ -43,7 +43,7 @@ SIGNATURES = {
     "ctc_vq_argmax": [P, P, I, I, P, P, I, P, P, P, P],
     "ctc_vq_gather_pool": [P, P, I, I, I, I, P, P, P, P],
     "ctc_vq_bwd": [P, P, P, I, I, I, I, I, P, P],
-    "ctc_latent_proj": [P, P, I, L, I, P, I, P, P],
+    "ctc_latent_proj": [P, P, P, I, L, I, P, I, P, P],
     "ctc_latent_proj_bwd": [P, P, I, L, I, P, P],
     "ctc_text_latent": [P, P, I, I, I, P, P],
     "ctc_latent_sim": [P, P, I, I, I, F, P, P, P, P],

@@ -320,7 +320,7 @@ class Engine:
         n_chunks = (L + 1023) // 1024
         partial = self._empty(n_chunks, B, NL)
         latent = self._empty(B, NL)
-        call("ctc_latent_proj", pooled, pl.wv_bf16, B, L, NL, partial, n_chunks, latent, stream_ptr())
+        call("ctc_latent_proj", pooled, pl.wv_bf16, pl.wv_lo_bf16, B, L, NL, partial, n_chunks, latent, stream_ptr())
         Bt = text_latents.shape[0]
         sim, il = self._empty(B, Bt), self._empty(B, NL)
         dlat = self._empty(B, NL) if save else None

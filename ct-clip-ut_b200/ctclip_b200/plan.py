@@ -112,7 +112,11 @@ class Plan:
         cb = f32(vt + "vq._codebook.embed")[0].contiguous()       # [K, C]
         self.codebook, self.codebook_bf16 = cb, _bf16(cb)
 
-        self.wv_bf16 = _bf16(f32("to_visual_latent.weight"))       # [NL, L]
+        wv = f32("to_visual_latent.weight")                         # [NL, L]
+        self.wv_bf16 = _bf16(wv)
+        # rounding residual of the bf16 weight: the forward projection uses hi + lo (see latent_proj_mma_kernel)
+        self.wv_lo_bf16 = _bf16(wv - self.wv_bf16.float())
+        del wv
         self.wt = f32("to_text_latent.weight")                     # [NL, DT]
         self.temp_exp = float(sd["temperature"].float().exp())
         torch.cuda.synchronize(dev)

