@@ -100,6 +100,11 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
+        # A/B switches of the measurement tools (defaults are the fastest measured variants)
+        if os.environ.get("CTC_ATTN_BWD"):
+            lib.ctc_attention_set_tc_bwd(int(os.environ["CTC_ATTN_BWD"]))
+        if os.environ.get("CTC_ATTN_EXP2_POLY"):
+            lib.ctc_attention_set_exp2_poly(int(os.environ["CTC_ATTN_EXP2_POLY"]))
         _lib = lib
     return _lib
 
