@@ -599,7 +599,9 @@ def run_product(args):
         s.record()
         r = orig_gemm(a, w, out, epi, bias=bias, resid=resid, aux=aux)
         e.record()
-        events.append((2.0 * a.shape[0] * algo(a.shape[1]) * algo(w.shape[0]), s, e, (a.shape[0], w.shape[0], a.shape[1])))
+        nbytes = sum(t.numel() * t.element_size() for t in (a, w, out, resid, aux) if t is not None)
+        events.append((2.0 * a.shape[0] * algo(a.shape[1]) * algo(w.shape[0]), s, e, (a.shape[0], w.shape[0], a.shape[1]), epi,
+                       nbytes))
         return r
     eng.gemm = timed_gemm
     step_device()
@@ -609,12 +611,29 @@ def run_product(args):
     gemm_ms = sum(ev[1].elapsed_time(ev[2]) for ev in events)
     gemm_shapes = [(*ev[3], ev[1].elapsed_time(ev[2])) for ev in events]
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12
+    # the same launches by epilogue: the fused epilogues carry HBM work that used to be separate passes (the fp32
+    # residual stream, the GEGLU adjoint factors), so their launches are HBM-bound by construction
+    epi_names = {0: "bf16 out", 1: "fp32 out + bias + residual", 3: "Linear + GEGLU (+ adjoint factors)", 4: "dh + GEGLU adjoint"}
+    by_epi = {}
+    # per-launch roofline max(FLOPs / tensor peak, compulsory bytes / HBM peak): the yardstick for a family in which the
+    # residual-stream and GEGLU-adjoint launches are HBM-bound by construction
+    mixed_ms = sum(max(ev[0] / (peaks["tf"] * 1e12), ev[5] / (peaks["hbm_gbs"] * 1e9)) for ev in events) * 1e3
+    for fl, s_, e_, _shape, epi, _nb in events:
+        d = by_epi.setdefault(epi_names.get(epi, str(epi)), {"launches": 0, "ms": 0.0, "flops": 0.0})
+        d["launches"] += 1
+        d["ms"] += s_.elapsed_time(e_)
+        d["flops"] += fl
+    for d in by_epi.values():
+        d["tflops"] = d.pop("flops") / (d["ms"] / 1e3) / 1e12
     traffic, traffic_src = ncu_gemm_traffic()
     roofline = {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf"],
                 "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
-                "launches_per_step": len(events), "gemm_ms_per_step": gemm_ms,
+                "launches_per_step": len(events), "gemm_ms_per_step": gemm_ms, "by_epilogue": by_epi,
+                "mixed_roofline": {"ms_at_roofline": mixed_ms, "frac": mixed_ms / gemm_ms,
+                                   "definition": "sum over the launches of max(FLOPs / bf16 peak, compulsory operand + output + "
+                                                 "residual + saved-factor bytes / HBM peak) / measured time"},
                 "share_of_step": gemm_ms / ms_step}
 
     # ---- the attribution sub-metric (occlusion sweep + IG-50 of one volume, sharded over the ranks)
