@@ -12,10 +12,15 @@
 //                  dS as bf16 -> TMEM dS[b] (A operand of the dQ MMA); P and dS as bf16 -> shared-memory staging tiles
 //                  in [key][query] order (K-major B operands of the dV / dK MMAs)
 //   MMA thread   : dQ[mt]  += dS K^                        (TS, A = dS from TMEM, B = K^ transposed tile)
-//                  dV^T[kt] += dO^T P,  dK^T[kt] += Q^^T dS (SS, A = resident transposed copies of dO / Q^ with the 32
-//                  head dims as rows 0-31 of an M = 128 operand - rows 32-127 read whatever follows in shared memory
-//                  and only produce accumulator lanes nobody reads -, B = the staging tiles, K = the 128 queries)
-//   drain warp   : per key tile, dV^T / dK^T -> transpose through shared memory -> dv rows, l2norm / k_scale adjoint -> dk
+//                  [dV^T ; dK^T][kt] += [dO^T ; Q^^T] [P ; dS]^T   ONE SS stream, M128 N64 K128: the A operand stacks the
+//                  resident transposed copies (rows 0-31 = dO^T, rows 32-63 = Q^^T of a 64-query block; rows 64-127 read
+//                  the next block and only produce accumulator lanes nobody reads), the B operand stacks the staging
+//                  tiles (rows 0-31 = P, 32-63 = dS), so accumulator lanes 0-31 x columns 0-31 hold dV^T and lanes 32-63
+//                  x columns 32-63 hold dK^T (the two off-diagonal blocks are by-products nobody reads)
+//   drain warps  : per key tile, dV^T / dK^T -> transpose through shared memory -> dv rows, l2norm / k_scale adjoint -> dk
+// S / dP of tile t+2 are issued as soon as the softmax warps have READ tile t (s_free), i.e. ahead of the dQ / dV / dK
+// products of tile t: the first version issued them behind those 18 MMAs and ncu showed 25 % of all warp samples on the
+// s_full wait (profiles/r02_ncu_attn_onepass.md).
 //   loader warp  : streams the 32-key K^ / V / K^T tiles (normalised on the fly) two tiles ahead
 // Everything that is summed is summed by the tensor core in issue order: no atomics, bit-reproducible.
 // D_i = rowsum(dO o O) and lse are staged once per CTA together with the resident Q^ / dO tiles and their transposes.
@@ -25,11 +30,12 @@ namespace ctc {
 
 static constexpr int OB_NK = 32;                                   // keys per tile
 static constexpr int OB_SOFTMAX_WARPS = 16;                        // four per TMEM lane quarter, 8 keys of the tile each
-static constexpr int OB_WARP_DRAIN = 16, OB_WARP_MMA = 17, OB_WARP_LOAD = 18;
-static constexpr int OB_THREADS = 19 * 32;
+static constexpr int OB_WARP_DRAIN_V = 16, OB_WARP_DRAIN_K = 17;    // warp % 4 = 0 / 1: TMEM lanes 0-31 (dV^T) / 32-63 (dK^T)
+static constexpr int OB_WARP_MMA = 18, OB_WARP_LOAD = 19;
+static constexpr int OB_THREADS = 20 * 32;
 static constexpr int OB_MAX_MT = 5;                                // n <= 640
 static constexpr uint32_t OB_TMEM_COLS = 512;
-static constexpr uint32_t OB_COL_S = 0, OB_COL_DP = 64, OB_COL_DS = 128, OB_COL_DQ = 160, OB_COL_DV = 320, OB_COL_DK = 384;
+static constexpr uint32_t OB_COL_S = 0, OB_COL_DP = 64, OB_COL_DS = 128, OB_COL_DQ = 160, OB_COL_DVK = 320;   // dVK: 2 x 64
 
 CTC_DEVINL void tmem_st_32x32b_x4(uint32_t taddr, const uint32_t (&r)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
@@ -38,24 +44,22 @@ CTC_DEVINL void tmem_st_32x32b_x4(uint32_t taddr, const uint32_t (&r)[4]) {
 }
 
 struct ObSmem {                                                    // byte offsets from the 1024-byte aligned base
-    int qs, dos, qT, doT, stgP, stgD, kt, pair, tab8, lse2, dl, sv, tr, bars, total;
+    int qs, dos, tT, stg, kt, pair, tab8, lse2, dl, sv, tr, bars, total;
 };
 CTC_DEVINL ObSmem __host__ ob_layout(int n_rows, int nb) {
     ObSmem L;
     int o = 0;
     L.qs = o;   o += n_rows * 64;                                  // [n_rows][64 B]  q^ * scale * log2e   SWIZZLE_64B
     L.dos = o;  o += n_rows * 64;                                  // [n_rows][64 B]  dO                   SWIZZLE_64B
-    L.qT = o;   o += (n_rows / 64) * 4096;                         // [n_rows/64][32][128 B]  (q^)^T       SWIZZLE_128B
-    L.doT = o;  o += (n_rows / 64) * 4096;                         //                          dO^T
-    L.stgP = o; o += 8192;                                         // [2][32 keys][128 B = 64 queries]     SWIZZLE_128B
-    L.stgD = o; o += 8192;
+    L.tT = o;   o += (n_rows / 64) * 8192;                         // [n_rows/64][64 rows: dO^T | (q^)^T][128 B]  SWIZZLE_128B
+    L.stg = o;  o += 2 * 8192;                                     // [2][64 rows: P keys | dS keys][128 B = 64 queries]
     L.kt = o;   o += 2 * 6144;                                     // [2] x { K^ 32 x 64 B | V | (K^)^T }  SWIZZLE_64B
     L.pair = o; o += ((nb + 1) & ~1) * 8;
     L.tab8 = o; o += ((n_rows / 8 + 3) & ~3) * 4;
     L.lse2 = o; o += n_rows * 4;
     L.dl = o;   o += n_rows * 4;
     L.sv = o;   o += 256;
-    L.tr = o;   o += 32 * 33 * 4;
+    L.tr = o;   o += 2 * 32 * 33 * 4;
     o = (o + 15) & ~15;
     L.bars = o; o += 256;
     L.total = o;
@@ -73,8 +77,8 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
     const int nW = 2 * p.W - 1, nb = (2 * p.H - 1) * nW;
     const ObSmem L = ob_layout(n_rows, nb);
     uint8_t* qs = smb + L.qs;   uint8_t* dos = smb + L.dos;
-    uint8_t* qT = smb + L.qT;   uint8_t* doT = smb + L.doT;
-    uint8_t* stgP = smb + L.stgP; uint8_t* stgD = smb + L.stgD;
+    uint8_t* tT = smb + L.tT;
+    uint8_t* stg = smb + L.stg;
     uint8_t* ktl = smb + L.kt;
     float2* pair = reinterpret_cast<float2*>(smb + L.pair);
     int* tab8 = reinterpret_cast<int*>(smb + L.tab8);
@@ -95,7 +99,7 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
             mbar_init(&s_full[b], 1);  mbar_init(&s_free[b], OB_SOFTMAX_WARPS);
             mbar_init(&p_full[b], OB_SOFTMAX_WARPS);  mbar_init(&ds_free[b], 1);
             mbar_init(&k_full[b], 1);  mbar_init(&k_free[b], 1);
-            mbar_init(&kv_full[b], 1); mbar_init(&kv_free[b], 1);
+            mbar_init(&kv_full[b], 1); mbar_init(&kv_free[b], 2);
         }
         mbar_init(stg_free, 1);
         mbar_init(dq_done, 1);
@@ -149,7 +153,7 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
             const uint8_t* src = (which ? dos : qs) + (r >> 7) * (TC_M * 64);
-            uint8_t* blk = (which ? doT : qT) + (r >> 6) * 4096 + (r & 7) * 2;
+            uint8_t* blk = tT + (r >> 6) * 8192 + (which ? 0 : 4096) + (r & 7) * 2;     // rows 0-31 dO^T, rows 32-63 (q^)^T
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint4 c = *reinterpret_cast<const uint4*>(src + tile_off(r & 127, q));
@@ -173,9 +177,9 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
 
     if (warp == OB_WARP_MMA) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(TC_M, OB_NK);
-            auto issue_s = [&](int t) {                               // S(t), dP(t) into buffer t & 1
-                const int kt = t / n_mt, mt = t - kt * n_mt, b = t & 1;
+            const uint32_t idesc = make_idesc_bf16(TC_M, OB_NK), idesc_vk = make_idesc_bf16(TC_M, 2 * OB_NK);
+            auto issue_s = [&](int t, int kt, int mt) {               // S(t), dP(t) into buffer t & 1
+                const int b = t & 1;
                 if (mt == 0) { mbar_wait(&k_full[kt & 1], (kt >> 1) & 1); tcgen05_fence_after(); }
                 if (t >= 2) { mbar_wait(&s_free[b], ((t >> 1) - 1) & 1); tcgen05_fence_after(); }
                 const uint8_t* kb = ktl + (kt & 1) * 6144;
@@ -190,38 +194,42 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
                 umma_f16_ss(tdp, dd + 2, dv + 2, idesc, 1u);
                 umma_commit(&s_full[b]);
             };
-            issue_s(0);
-            if (n_tiles > 1) issue_s(1);
-            for (int t = 0; t < n_tiles; ++t) {
-                const int kt = t / n_mt, mt = t - kt * n_mt, b = t & 1;
-                mbar_wait(&p_full[b], (t >> 1) & 1);                  // dS(t) in TMEM, P / dS staged
-                if (mt == 0 && kt >= 2) mbar_wait(&kv_free[kt & 1], ((kt >> 1) - 1) & 1);   // accumulators drained
-                tcgen05_fence_after();
+            // (kt, mt) of tile t + 2, advanced alongside the loop (no integer divisions in the tile stream)
+            int kt2 = 0, mt2 = 0;
+            auto advance2 = [&]() { if (++mt2 == n_mt) { mt2 = 0; ++kt2; } };
+            issue_s(0, kt2, mt2); advance2();
+            if (n_tiles > 1) { issue_s(1, kt2, mt2); advance2(); }
+            int t = 0;
+            for (int kt = 0; kt < n_kt; ++kt) {
                 const uint8_t* kb = ktl + (kt & 1) * 6144;
-                // dQ[mt] += dS K^
                 const uint64_t dkT = make_umma_desc_sw64(smem_u32(kb + 4096));
-                const uint32_t tds = tmem_base + OB_COL_DS + b * (OB_NK / 2);
-                const uint32_t tdq = tmem_base + OB_COL_DQ + mt * DH;
+                const uint32_t tvk = tmem_base + OB_COL_DVK + (kt & 1) * (2 * OB_NK);
+                for (int mt = 0; mt < n_mt; ++mt, ++t) {
+                    const int b = t & 1;
+                    // S / dP of tile t + 2 first: they only need the softmax warps to have READ tile t (s_free)
+                    if (t + 2 < n_tiles) { issue_s(t + 2, kt2, mt2); advance2(); }
+                    mbar_wait(&p_full[b], (t >> 1) & 1);              // dS(t) in TMEM, P / dS staged
+                    if (mt == 0 && kt >= 2) mbar_wait(&kv_free[kt & 1], ((kt >> 1) - 1) & 1);   // accumulators drained
+                    tcgen05_fence_after();
+                    // dQ[mt] += dS K^
+                    const uint32_t tds = tmem_base + OB_COL_DS + b * (OB_NK / 2);
+                    const uint32_t tdq = tmem_base + OB_COL_DQ + mt * DH;
 #pragma unroll
-                for (int kk = 0; kk < OB_NK / 16; ++kk)
-                    umma_f16_ts(tdq, tds + kk * 8, dkT + (uint64_t)(kk * 2), idesc, (kt > 0 || kk > 0) ? 1u : 0u);
-                umma_commit(&ds_free[b]);
-                // dV^T[kt] += dO^T P ; dK^T[kt] += (Q^)^T dS      (reduction over the 128 queries of the M-tile)
-                const uint32_t tdv = tmem_base + OB_COL_DV + (kt & 1) * OB_NK, tdk = tmem_base + OB_COL_DK + (kt & 1) * OB_NK;
+                    for (int kk = 0; kk < OB_NK / 16; ++kk)
+                        umma_f16_ts(tdq, tds + kk * 8, dkT + (uint64_t)(kk * 2), idesc, (kt > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&ds_free[b]);
+                    // [dV^T ; dK^T][kt] += [dO^T ; Q^^T](mt) [P ; dS](t)^T    (reduction over the 128 queries of the M-tile)
+                    const uint64_t a0 = make_umma_desc_sw128(smem_u32(tT) + (uint32_t)(mt * 2) * 8192u);
+                    const uint64_t b0 = make_umma_desc_sw128(smem_u32(stg));
 #pragma unroll
-                for (int kk = 0; kk < TC_M / 16; ++kk) {
-                    const uint32_t blk = (uint32_t)(mt * 2 + (kk >> 2)) * 4096u;
-                    const uint64_t koff = (uint64_t)((kk & 3) * 2);
-                    const uint64_t aP = make_umma_desc_sw128(smem_u32(doT) + blk) + koff;
-                    const uint64_t bP = make_umma_desc_sw128(smem_u32(stgP) + (uint32_t)(kk >> 2) * 4096u) + koff;
-                    umma_f16_ss(tdv, aP, bP, idesc, (mt > 0 || kk > 0) ? 1u : 0u);
-                    const uint64_t aD = make_umma_desc_sw128(smem_u32(qT) + blk) + koff;
-                    const uint64_t bD = make_umma_desc_sw128(smem_u32(stgD) + (uint32_t)(kk >> 2) * 4096u) + koff;
-                    umma_f16_ss(tdk, aD, bD, idesc, (mt > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < TC_M / 16; ++kk) {
+                        // +512 in the (addr >> 4) field = the next 8 KB block; +2 = the next 16 queries (32 B) of a row
+                        const uint64_t off = (uint64_t)((kk >> 2) * 512 + (kk & 3) * 2);
+                        umma_f16_ss(tvk, a0 + off, b0 + off, idesc_vk, (mt > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(stg_free);
+                    if (mt == n_mt - 1) { umma_commit(&kv_full[kt & 1]); umma_commit(&k_free[kt & 1]); }
                 }
-                umma_commit(stg_free);
-                if (mt == n_mt - 1) { umma_commit(&kv_full[kt & 1]); umma_commit(&k_free[kt & 1]); }
-                if (t + 2 < n_tiles) issue_s(t + 2);
             }
             umma_commit(dq_done);
         }
@@ -268,40 +276,36 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&k_full[kt & 1]);
         }
-    } else if (warp == OB_WARP_DRAIN) {
-        // dV^T / dK^T of key tile kt: lane = head dim d (TMEM lanes 0-31), 32 columns = keys
+    } else if (warp == OB_WARP_DRAIN_V || warp == OB_WARP_DRAIN_K) {
+        // dV^T (TMEM lanes 0-31, columns 0-31) / dK^T (lanes 32-63, columns 32-63) of key tile kt: lane = head dim
+        const bool is_k = warp == OB_WARP_DRAIN_K;
+        float* trw = tr + (is_k ? 32 * 33 : 0);
+        const uint32_t tsel = is_k ? (((uint32_t)32 << 16) + OB_NK) : 0u;
         for (int kt = 0; kt < n_kt; ++kt) {
             const int b2 = kt & 1;
             mbar_wait(&kv_full[b2], (kt >> 1) & 1);
             tcgen05_fence_after();
-            uint32_t av[32], ak[32];
-            tmem_ld_32x32b_x32(tmem_base + OB_COL_DV + b2 * OB_NK, av);
-            tmem_ld_32x32b_x32(tmem_base + OB_COL_DK + b2 * OB_NK, ak);
+            uint32_t av[32];
+            tmem_ld_32x32b_x32(tmem_base + OB_COL_DVK + b2 * (2 * OB_NK) + tsel, av);
             tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&kv_free[b2]);
-            const long long row = seq_row(p, s, kt * OB_NK + lane);      // after the transposes: lane = key
-            // ---- dV
+            const long long row = seq_row(p, s, kt * OB_NK + lane);      // after the transpose: lane = key
 #pragma unroll
-            for (int c = 0; c < 32; ++c) tr[c * 33 + lane] = __uint_as_float(av[c]);
+            for (int c = 0; c < 32; ++c) trw[c * 33 + lane] = __uint_as_float(av[c]);
             __syncwarp();
-            {
+            if (!is_k) {
                 uint4* drow = reinterpret_cast<uint4*>(p.dv + row * p.lddkv + head * DH);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint32_t w[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) w[e] = pack_bf16(tr[lane * 33 + j * 8 + e * 2], tr[lane * 33 + j * 8 + e * 2 + 1]);
+                    for (int e = 0; e < 4; ++e) w[e] = pack_bf16(trw[lane * 33 + j * 8 + e * 2], trw[lane * 33 + j * 8 + e * 2 + 1]);
                     drow[j] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-            }
-            __syncwarp();
-            // ---- dK: accumulated against q^ * scale * log2e -> undo log2e; k_scale and the l2norm adjoint
-#pragma unroll
-            for (int c = 0; c < 32; ++c) tr[c * 33 + lane] = __uint_as_float(ak[c]);
-            __syncwarp();
-            {
+            } else {
+                // accumulated against q^ * scale * log2e -> undo log2e; k_scale and the l2norm adjoint
                 const uint4* gk = reinterpret_cast<const uint4*>(p.k + row * p.ldkv + head * DH);
                 float x[32], g[32];
                 float ss = 0.f;
@@ -320,7 +324,7 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
                 float dot = 0.f;
 #pragma unroll
                 for (int dd = 0; dd < 32; ++dd) {
-                    g[dd] = tr[lane * 33 + dd] * LN2 * sv[32 + dd];
+                    g[dd] = trw[lane * 33 + dd] * LN2 * sv[32 + dd];
                     x[dd] *= inv;
                     dot += x[dd] * g[dd];
                 }
@@ -342,52 +346,66 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
         const int quarter = warp & 3, cpart = warp >> 2;              // TMEM lane quarter; 8-key slice of the 32-key tile
         const int r = quarter * 32 + lane;                            // query row of the M-tile = TMEM lane
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        const int sblk = (r >> 6) * 4096, sch = (r & 63) >> 3, sslot = (r & 7) * 2;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int kt = t / n_mt, mt = t - kt * n_mt, b = t & 1;
-            const int i = mt * TC_M + r;
-            const int base_i = bias_base(p, i);
-            const float lse2_i = lse2[i], d_i = dl[i];
-            const int tb0 = tab8[(kt * OB_NK + cpart * 8) >> 3];
-            mbar_wait(&s_full[b], (t >> 1) & 1);
-            tcgen05_fence_after();
-            uint32_t vs_[8], vd_[8];
-            tmem_ld_32x32b_x8(tmem_base + OB_COL_S + b * OB_NK + lane_sel + cpart * 8, vs_);
-            tmem_ld_32x32b_x8(tmem_base + OB_COL_DP + b * OB_NK + lane_sel + cpart * 8, vd_);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[b]);                   // S / dP buffer b may be overwritten (tile t + 2)
-            uint32_t pkP[4], pkD[4];
+        // per-thread constants of the tile stream, computed once: the bias-table base of this thread's row in every
+        // M-tile, and the staging addresses of its 8 keys (P row c, dS row 32 + c of the 64-query block r / 64)
+        int base_m[OB_MAX_MT];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float2 f = pair[base_i - tb0 - 2 * u];
-                const float p0 = fast_exp2(__uint_as_float(vs_[2 * u]) + f.x - lse2_i);
-                const float p1 = fast_exp2(__uint_as_float(vs_[2 * u + 1]) + f.y - lse2_i);
-                pkP[u] = pack_bf16(p0, p1);
-                pkD[u] = pack_bf16(p0 * (__uint_as_float(vd_[2 * u]) - d_i), p1 * (__uint_as_float(vd_[2 * u + 1]) - d_i));
-            }
-            if (t >= 2) {                                             // dS(t-2) consumed by its dQ MMAs
-                mbar_wait(&ds_free[b], ((t >> 1) - 1) & 1);
+        for (int m = 0; m < OB_MAX_MT; ++m) base_m[m] = bias_base(p, m * TC_M + r);
+        uint32_t soff[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            soff[k] = smem_u32(stg) + (uint32_t)((r >> 6) * 8192 + (cpart * 8 + k) * 128 + ((((r & 63) >> 3) ^ k) << 4) + (r & 7) * 2);
+        const uint32_t ts0 = tmem_base + OB_COL_S + lane_sel + cpart * 8, tdp0 = tmem_base + OB_COL_DP + lane_sel + cpart * 8;
+        const uint32_t tds0 = tmem_base + OB_COL_DS + lane_sel + cpart * 4;
+        int t = 0;
+        for (int kt = 0; kt < n_kt; ++kt) {
+            const int tb0 = tab8[kt * (OB_NK / 8) + cpart];
+#pragma unroll 1
+            for (int mt = 0; mt < n_mt; ++mt, ++t) {
+                const int b = t & 1;
+                const int i = mt * TC_M + r;
+                // select chain instead of base_m[mt]: a dynamically indexed array would live in local memory
+                const int base_i = mt == 0 ? base_m[0] : mt == 1 ? base_m[1] : mt == 2 ? base_m[2] : mt == 3 ? base_m[3] : base_m[4];
+                const float2* prow = pair + (base_i - tb0);
+                const float lse2_i = lse2[i], d_i = dl[i];
+                mbar_wait(&s_full[b], (t >> 1) & 1);
                 tcgen05_fence_after();
-            }
-            tmem_st_32x32b_x4(tmem_base + OB_COL_DS + b * (OB_NK / 2) + lane_sel + cpart * 4, pkD);
-            if (t >= 1) mbar_wait(stg_free, (t - 1) & 1);             // staging consumed by the dV / dK MMAs of tile t-1
+                uint32_t vs_[8], vd_[8];
+                tmem_ld_32x32b_x8(ts0 + b * OB_NK, vs_);
+                tmem_ld_32x32b_x8(tdp0 + b * OB_NK, vd_);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[b]);               // S / dP buffer b may be overwritten (tile t + 2)
+                uint32_t pkP[4], pkD[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = cpart * 8 + 2 * u + h;              // key row of the staging tile
-                    const int off = sblk + c * 128 + ((sch ^ (c & 7)) << 4) + sslot;
-                    *reinterpret_cast<uint16_t*>(stgP + off) = (uint16_t)(h ? (pkP[u] >> 16) : (pkP[u] & 0xFFFFu));
-                    *reinterpret_cast<uint16_t*>(stgD + off) = (uint16_t)(h ? (pkD[u] >> 16) : (pkD[u] & 0xFFFFu));
+                for (int u = 0; u < 4; ++u) {
+                    const float2 f = prow[-2 * u];
+                    const float p0 = fast_exp2(__uint_as_float(vs_[2 * u]) + f.x - lse2_i);
+                    const float p1 = fast_exp2(__uint_as_float(vs_[2 * u + 1]) + f.y - lse2_i);
+                    pkP[u] = pack_bf16(p0, p1);
+                    pkD[u] = pack_bf16(p0 * (__uint_as_float(vd_[2 * u]) - d_i), p1 * (__uint_as_float(vd_[2 * u + 1]) - d_i));
                 }
+                if (t >= 2) {                                         // dS(t-2) consumed by its dQ MMAs
+                    mbar_wait(&ds_free[b], ((t >> 1) - 1) & 1);
+                    tcgen05_fence_after();
+                }
+                tmem_st_32x32b_x4(tds0 + b * (OB_NK / 2), pkD);
+                if (t >= 1) mbar_wait(stg_free, (t - 1) & 1);         // staging consumed by the dV / dK MMAs of tile t-1
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    // st.shared.u16 stores the low half of the register: the odd key needs one shift
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(soff[2 * u]), "h"((uint16_t)(pkP[u] & 0xFFFFu)) : "memory");
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(soff[2 * u + 1]), "h"((uint16_t)(pkP[u] >> 16)) : "memory");
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(soff[2 * u] + 4096u), "h"((uint16_t)(pkD[u] & 0xFFFFu)) : "memory");
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(soff[2 * u + 1] + 4096u), "h"((uint16_t)(pkD[u] >> 16)) : "memory");
+                }
+                tmem_st_wait();
+                fence_proxy_async();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[b]);
             }
-            tmem_st_wait();
-            fence_proxy_async();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[b]);
         }
         if (cpart == 0) {                                             // one warp per lane quarter finishes the dQ rows
             mbar_wait(dq_done, 0);

@@ -465,19 +465,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             const float x0 = __uint_as_float(xv[2 * j]), x1 = __uint_as_float(xv[2 * j + 1]);
                             const float g0 = __uint_as_float(gv[2 * j]), g1 = __uint_as_float(gv[2 * j + 1]);
                             float c0, p0, c1, p1;
-                            gelu_parts(g0, c0, p0);
-                            gelu_parts(g1, c1, p1);
+                            gelu_parts_fast(g0, c0, p0);
+                            gelu_parts_fast(g1, c1, p1);
                             const float a0 = g0 * c0, a1 = g1 * c1;
                             hk[j] = pack_bf16(a0 * x0, a1 * x1);
-                            pk[j] = pack_bf16(a0, a1);
-                            pk[16 + j] = pack_bf16(x0 * fmaf(g0, p0, c0), x1 * fmaf(g1, p1, c1));
+                            pk[j] = pack_bf16_alu(a0, a1);                     // the saved factors are packed on the ALU pipe
+                            pk[16 + j] = pack_bf16_alu(x0 * fmaf(g0, p0, c0), x1 * fmaf(g1, p1, c1));
                         }
                         epilogue_bf16_staged(g, stage, row0, col0, lane, pk, uout, g.ldaux);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            hk[j] = pack_bf16(gelu_erf(__uint_as_float(gv[2 * j])) * __uint_as_float(xv[2 * j]),
-                                              gelu_erf(__uint_as_float(gv[2 * j + 1])) * __uint_as_float(xv[2 * j + 1]));
+                        for (int j = 0; j < 16; ++j) {
+                            // same arithmetic as the branch above, so that h does not depend on whether u is saved
+                            const float g0 = __uint_as_float(gv[2 * j]), g1 = __uint_as_float(gv[2 * j + 1]);
+                            float c0, p0, c1, p1;
+                            gelu_parts_fast(g0, c0, p0);
+                            gelu_parts_fast(g1, c1, p1);
+                            hk[j] = pack_bf16((g0 * c0) * __uint_as_float(xv[2 * j]), (g1 * c1) * __uint_as_float(xv[2 * j + 1]));
+                        }
                     }
                     epilogue_bf16_staged32(g, stage, row0, col0 / 2, lane, hk, hout, g.ldc);
                 }
@@ -728,7 +733,9 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
     // the reduction and the output are wide (to_kv, FF2, dh, dxn2, patch embedding and its adjoint) and lose 3-6 % on the
     // narrow to_q / to_out launches and under the arithmetic-heavy GEGLU epilogue, where the leader's MMA issue has to
     // wait for the slower of two epilogues; impl = CTC_GEMM_TCGEN05_PAIR forces pairs everywhere (tests).
-    const bool want_pair = impl == CTC_GEMM_TCGEN05_PAIR || (pair_env && K >= 512 && N >= 512 && epi != CTC_EPI_GEGLU);
+    // The VQ score GEMM (N = 8192, K = 512, top-2 epilogue) also prefers single CTAs: 749 us in pairs vs 652 us.
+    const bool want_pair = impl == CTC_GEMM_TCGEN05_PAIR ||
+                           (pair_env && K >= 512 && N >= 512 && epi != CTC_EPI_GEGLU && epi != CTC_EPI_ARGMAX);
     const bool pair = bn256 && impl != CTC_GEMM_TCGEN05_1CTA && want_pair && (num_sms() % 2 == 0);
     g.n_tiles_n = (N + BNsel - 1) / BNsel;
     CUtensorMap ta, tb;

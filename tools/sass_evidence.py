@@ -1,6 +1,6 @@
 """Count the SASS mnemonics that prove tcgen05 / TMEM / TMA / mbarrier use, per kernel of the built library, plus each
 kernel's register count and static shared memory (cuobjdump; no GPU needed).
-    python tools/sass_evidence.py > profiles/r01_sass_evidence.md"""
+    python tools/sass_evidence.py > profiles/r02_sass_evidence.md"""
 import re
 import subprocess
 import sys
@@ -9,7 +9,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 SO = ROOT / "ct-clip-ut_b200" / "ctclip_b200" / "libctclip_b200.so"
-PAT = OrderedDict([("UTC*MMA (tcgen05.mma)", r"\bUTC\w*MMA"), ("UTCBAR / UTCCP (tcgen05 commit / cp)", r"\bUTC(BAR|CP)"),
+PAT = OrderedDict([("UTC*MMA (tcgen05.mma)", r"\bUTC\w*MMA"), ("UTC*MMA.2CTA (cta_group::2)", r"\bUTC\w*MMA\.2CTA"),
+                   ("UTMALDG.*.2CTA", r"\bUTMALDG\.\w+\.2CTA"), ("UTCBAR.2CTA.MULTICAST", r"\bUTCBAR\.2CTA\.MULTICAST"), ("UTCBAR / UTCCP (tcgen05 commit / cp)", r"\bUTC(BAR|CP)"),
                    ("LDTM / STTM (tcgen05.ld / st)", r"\b(LDTM|STTM)"), ("UTMALDG / UTMASTG / UBLKCP (TMA)", r"\b(UTMALDG|UTMASTG|UBLKCP)"),
                    ("SYNCS (mbarrier)", r"\bSYNCS"), ("LDGSTS (cp.async)", r"\bLDGSTS"), ("HMMA (mma.sync)", r"\bHMMA"),
                    ("MUFU.EX2", r"\bMUFU\.EX2")])
@@ -56,7 +57,7 @@ rest = []
 for n in names:
     c = kernels[n]
     r, s = usage.get(n, ("?", "?"))
-    if any(c[k] for k in cols[:6]):
+    if any(c[k] for k in cols[:9]):
         print(f"| `{pretty[n]}` | {r} | {s} | " + " | ".join(str(c[k]) for k in cols) + " |")
     else:
         rest.append((pretty[n], r, s, c["HMMA (mma.sync)"], c["MUFU.EX2"]))
