@@ -199,6 +199,9 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
             auto advance2 = [&]() { if (++mt2 == n_mt) { mt2 = 0; ++kt2; } };
             issue_s(0, kt2, mt2); advance2();
             if (n_tiles > 1) { issue_s(1, kt2, mt2); advance2(); }
+            // With ONE M-tile per key tile, tile t + 2 belongs to key tile kt + 2, whose K buffer is the one tile t still
+            // reads: issuing it ahead would wait on a k_full that only this thread's own k_free commit can produce.
+            const bool ahead = n_mt >= 2;
             int t = 0;
             for (int kt = 0; kt < n_kt; ++kt) {
                 const uint8_t* kb = ktl + (kt & 1) * 6144;
@@ -207,7 +210,7 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
                 for (int mt = 0; mt < n_mt; ++mt, ++t) {
                     const int b = t & 1;
                     // S / dP of tile t + 2 first: they only need the softmax warps to have READ tile t (s_free)
-                    if (t + 2 < n_tiles) { issue_s(t + 2, kt2, mt2); advance2(); }
+                    if (ahead && t + 2 < n_tiles) { issue_s(t + 2, kt2, mt2); advance2(); }
                     mbar_wait(&p_full[b], (t >> 1) & 1);              // dS(t) in TMEM, P / dS staged
                     if (mt == 0 && kt >= 2) mbar_wait(&kv_free[kt & 1], ((kt >> 1) - 1) & 1);   // accumulators drained
                     tcgen05_fence_after();
@@ -229,6 +232,7 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
                     }
                     umma_commit(stg_free);
                     if (mt == n_mt - 1) { umma_commit(&kv_full[kt & 1]); umma_commit(&k_free[kt & 1]); }
+                    if (!ahead && t + 2 < n_tiles) { issue_s(t + 2, kt2, mt2); advance2(); }
                 }
             }
             umma_commit(dq_done);
