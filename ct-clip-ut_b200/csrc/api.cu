@@ -33,6 +33,7 @@ extern "C" int ctc_device_check(void) {
     return 0;
 }
 
+extern "C" int ctc_gemm_row_perm(int* perm32) { return gemm_row_perm(perm32); }
 extern "C" int ctc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldc, int M,
                              int N, int K, int epi, const float* bias, const float* resid, int64_t ldr, void* aux,
                              int64_t ldaux, int impl, void* stream) {

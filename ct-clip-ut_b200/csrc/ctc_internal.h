@@ -10,6 +10,7 @@ namespace ctc {
 int num_sms();
 
 // gemm.cu
+int gemm_row_perm(int* perm32);
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldc, int M, int N,
               int K, int epi, const float* bias, const float* resid, long long ldr, void* aux, long long ldaux,
               float* top2_val, int* top2_idx, int impl, cudaStream_t st);

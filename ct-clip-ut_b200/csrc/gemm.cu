@@ -35,8 +35,7 @@ namespace ctc {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int kEpiWarps = 8;
-static constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
+static constexpr int kEpiWarps = 8;       // default; the arithmetic-heavy GEGLU epilogue runs with 16 (template parameter EW)
 
 struct GemmArgs {
     int M, N, K;
@@ -52,13 +51,14 @@ struct GemmArgs {
     int n_tiles_n;
 };
 
-template <int BN, int CG>
+template <int BN, int CG, int EW = kEpiWarps, int DS = 0>
 struct GemmSmem {
-    static constexpr int kStages = CG == 2 ? 6 : 4;
+    static constexpr int kStages = CG == 2 ? (DS ? 7 : 6) : 4;      // direct epilogues need no staging tile: one more stage
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = (BN / CG) * BK * 2;          // pair mode: each CTA stages half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStageOut = kEpiWarps * 4096;       // epilogue staging: per warp 32 rows x 128 B
+    static constexpr int kStageWarp = EW == 16 ? 2048 : 4096;   // epilogue staging per warp: 32 rows x 128 B (64 B with 16 warps)
+    static constexpr int kStageOut = DS ? 0 : EW * kStageWarp;
     static constexpr int kOutOffset = kStages * kStageBytes;
     static constexpr int kBarOffset = kOutOffset + kStageOut;
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
@@ -132,24 +132,36 @@ CTC_DEVINL void epilogue_store(const GemmArgs& g, int row, int col0, const uint3
 // segments: residual / bias loads and the final stores are fully coalesced.
 // ---------------------------------------------------------------------------------------------
 CTC_DEVINL uint32_t stage_off(int row, int unit) { return (uint32_t)(row * 128 + ((unit ^ (row & 7)) << 4)); }
+// The staging tile is addressed in the shared state space explicitly: through generic pointers the compiler has to
+// assume that a global store may alias the next staging load and serialises every load / store pair of the read-out
+// (ncu: LD.E.128 -> wait -> STG -> LD ... , `long scoreboard` on each store); with ld.shared the eight loads of a
+// read-out are issued back to back.
+CTC_DEVINL void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+CTC_DEVINL uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
 // fp32 chunk: 32 rows x 32 columns
-CTC_DEVINL void epilogue_f32_staged(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
+CTC_DEVINL void epilogue_f32_staged(const GemmArgs& g, uint32_t stage, int row0, int col0, int lane,
                                     const uint32_t (&acc)[32], const float4 (&res)[8], bool has_res) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-        *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
-            make_uint4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+    for (int u = 0; u < 8; ++u) sts128(stage + stage_off(lane, u), acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
     __syncwarp();
     const int u = lane & 7;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g.bias) b = *reinterpret_cast<const float4*>(g.bias + col0 + u * 4);
+    uint4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = lds128(stage + stage_off((lane >> 3) + 4 * i, u));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int rl = (lane >> 3) + 4 * i;
-        const int row = row0 + rl;
-        float4 v = *reinterpret_cast<const float4*>(stage + stage_off(rl, u));
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        const int row = row0 + (lane >> 3) + 4 * i;
+        float4 v = make_float4(__uint_as_float(t[i].x) + b.x, __uint_as_float(t[i].y) + b.y, __uint_as_float(t[i].z) + b.z,
+                               __uint_as_float(t[i].w) + b.w);
         if (has_res) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
         if (row < g.M)
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (long long)row * g.ldc + col0 + u * 4) = v;
@@ -166,59 +178,64 @@ CTC_DEVINL void prefetch_resid(const GemmArgs& g, int row0, int col0, int lane, 
     }
 }
 // bf16 chunk: 32 rows x 64 columns (acc already packed to 32 x bf16x2) -> dst[row, col0 .. col0+64)
-CTC_DEVINL void epilogue_bf16_staged(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
+CTC_DEVINL void epilogue_bf16_staged(const GemmArgs& g, uint32_t stage, int row0, int col0, int lane,
                                      const uint32_t (&pk)[32], __nv_bfloat16* dst = nullptr, long long ld = 0) {
     if (!dst) { dst = reinterpret_cast<__nv_bfloat16*>(g.out); ld = g.ldc; }
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-        *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
-            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    for (int u = 0; u < 8; ++u) sts128(stage + stage_off(lane, u), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
     __syncwarp();
     const int u = lane & 7;
+    uint4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = lds128(stage + stage_off((lane >> 3) + 4 * i, u));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int rl = (lane >> 3) + 4 * i;
-        const int row = row0 + rl;
-        const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(rl, u));
-        if (row < g.M) *reinterpret_cast<uint4*>(dst + (long long)row * ld + col0 + u * 8) = v;
+        const int row = row0 + (lane >> 3) + 4 * i;
+        if (row < g.M) *reinterpret_cast<uint4*>(dst + (long long)row * ld + col0 + u * 8) = t[i];
     }
     __syncwarp();
 }
 // bf16 half chunk: 32 rows x 32 columns (16 x bf16x2 per thread) -> dst[row, col0 .. col0+32); 8 rows x 64 B per access
-CTC_DEVINL void epilogue_bf16_staged32(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
+CTC_DEVINL void epilogue_bf16_staged32(const GemmArgs& g, uint32_t stage, int row0, int col0, int lane,
                                        const uint32_t (&pk)[16], __nv_bfloat16* dst, long long ld) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-        *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
-            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    for (int u = 0; u < 4; ++u) sts128(stage + stage_off(lane, u), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
     __syncwarp();
     const int u = lane & 3;
+    uint4 t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = lds128(stage + stage_off((lane >> 2) + 8 * i, u));
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int rl = (lane >> 2) + 8 * i;
-        const int row = row0 + rl;
-        const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(rl, u));
-        if (row < g.M) *reinterpret_cast<uint4*>(dst + (long long)row * ld + col0 + u * 8) = v;
-    }
-    __syncwarp();
-}
-// coalesced load of a 32-row x 128-byte chunk (src[row, col0 .. col0+64) bf16) into the swizzled staging tile
-CTC_DEVINL void stage_load_bf16_64(const GemmArgs& g, uint8_t* stage, int row0, int col0, int lane,
-                                   const __nv_bfloat16* src, long long ld) {
-    const int u = lane & 7;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int rl = (lane >> 3) + 4 * i;
-        const int row = row0 + rl;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (row < g.M) v = *reinterpret_cast<const uint4*>(src + (long long)row * ld + col0 + u * 8);
-        *reinterpret_cast<uint4*>(stage + stage_off(rl, u)) = v;
+        const int row = row0 + (lane >> 2) + 8 * i;
+        if (row < g.M) *reinterpret_cast<uint4*>(dst + (long long)row * ld + col0 + u * 8) = t[i];
     }
     __syncwarp();
 }
 
-// the same load split in two halves, so that the global loads of the NEXT chunk are in flight (in registers) while the
-// current chunk is processed: issue (global -> registers) ... later ... commit (registers -> swizzled staging tile)
+// 16-warp epilogues: 2 KB per warp, 32 rows x 64 bytes (four 16-byte units per row).  Thread = row writes its 16 packed
+// words, then lane (row = lane / 4 + 8 i, unit = lane % 4) stores unit `unit` of four rows at dst + row * ld + col
+// (`col` chosen by the caller per unit: the adjoint factors a | b live 32 columns apart).
+CTC_DEVINL uint32_t stage_off64(int row, int unit) { return (uint32_t)(row * 64 + ((unit ^ ((row >> 1) & 3)) << 4)); }
+CTC_DEVINL void staged64_store(const GemmArgs& g, uint32_t stage, int row0, int lane, const uint32_t (&pk)[16],
+                               __nv_bfloat16* dst, long long ld, int col) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sts128(stage + stage_off64(lane, u), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    __syncwarp();
+    uint4 t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = lds128(stage + stage_off64((lane >> 2) + 8 * i, lane & 3));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = row0 + (lane >> 2) + 8 * i;
+        if (row < g.M) *reinterpret_cast<uint4*>(dst + (long long)row * ld + col) = t[i];
+    }
+    __syncwarp();
+}
+
+// coalesced global load of a 32-row x 128-byte chunk (src[row, col0 .. col0+64) bf16), split in two halves so that the
+// loads of the NEXT chunk are in flight (in registers) while the current chunk is processed:
+// issue (global -> registers) ... later ... commit (registers -> swizzled staging tile)
 CTC_DEVINL void stage_load_issue(const GemmArgs& g, int row0, int col0, int lane, const __nv_bfloat16* src, long long ld,
                                  uint4 (&reg)[8]) {
     const int u = lane & 7;
@@ -228,11 +245,210 @@ CTC_DEVINL void stage_load_issue(const GemmArgs& g, int row0, int col0, int lane
         reg[i] = (row < g.M) ? *reinterpret_cast<const uint4*>(src + (long long)row * ld + col0 + u * 8) : make_uint4(0, 0, 0, 0);
     }
 }
-CTC_DEVINL void stage_load_commit(uint8_t* stage, int lane, const uint4 (&reg)[8]) {
+CTC_DEVINL void stage_load_commit(uint32_t stage, int lane, const uint4 (&reg)[8]) {
     const int u = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stage + stage_off((lane >> 3) + 4 * i, u)) = reg[i];
+    for (int i = 0; i < 8; ++i) sts128(stage + stage_off((lane >> 3) + 4 * i, u), reg[i].x, reg[i].y, reg[i].z, reg[i].w);
     __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// direct epilogue (DS = 1): no shared-memory staging.
+// The staged read-out above costs shared-memory bandwidth the tensor core needs: at K <= 512 a 128 x 256 tile reads
+// 384 KB of operands from shared memory and TMA writes the same 384 KB, and the staging added up to 256 KB more per tile
+// (timing experiment with the staging accesses removed, tools/gpu/r2j.sh: FF1 + GEGLU 278 -> 222 us, + factors 364 -> 296
+// us, dh + adjoint 291 -> 210 us).  tcgen05.ld.16x256b hands a thread two adjacent columns of rows r and r + 8 for every
+// 8-column group (the mma.sync C-fragment layout); with the rows of the B operand permuted INSIDE every 32-row group at
+// plan time (ctc_gemm_row_perm) those 8 values per row are 8 consecutive output channels, i.e. one 16-byte store per row
+// (bf16), and the four threads of a row write 64 contiguous bytes: every store instruction covers eight
+// rows x two full 32-byte sectors (fp32: one 256-bit store per row, eight rows x a full 128-byte line).
+// Accumulator column a = 8 j + 2 q + e of a 32-column group holds channel 8 q + 2 j + e of the group.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int row_perm(int a) {
+    const int j = a >> 3, q = (a >> 1) & 3, e = a & 1;
+    return 8 * q + 2 * j + e;
+}
+// 16 lanes x 32 consecutive fp32 columns: register 4 j + 2 h + e = (lane base + 8 h + thread / 4, column 8 j + 2 (thread % 4) + e)
+CTC_DEVINL void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+CTC_DEVINL float asf(uint32_t v) { return __uint_as_float(v); }
+// 256-bit global accesses (sm_100: LDG / STG .256): 32 bytes per thread, so that the four threads that share a row in the
+// 16x256b register layout cover a full 128-byte line per instruction
+CTC_DEVINL void stg256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+                 "r"(f), "r"(g), "r"(h) : "memory");
+}
+CTC_DEVINL void ldg256(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]),
+                 "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+
+// taddr: this warp's lane quarter of the accumulator (column 0 of the tile); row0: first of its 32 rows;
+// colbase: first output column of the tile; [cbeg, cend): this warp's accumulator columns
+template <int EPI>
+CTC_DEVINL void epilogue_direct(const GemmArgs& g, uint32_t taddr, int row0, int colbase, int cbeg, int cend, int lane) {
+    const int r4 = lane >> 2, q = lane & 3;
+    if constexpr (EPI == CTC_EPI_BF16) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(g.out);
+#pragma unroll 1
+        for (int c = cbeg; c < cend; c += 32) {
+            const int col0 = colbase + c;
+            if (col0 >= g.N) break;
+            uint32_t v[2][16];
+            tmem_ld_16x256b_x4(taddr + c, v[0]);
+            tmem_ld_16x256b_x4(taddr + (16u << 16) + c, v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = row0 + 16 * L + 8 * h + r4;
+                    uint4 o;
+                    o.x = pack_bf16(asf(v[L][2 * h]), asf(v[L][2 * h + 1]));
+                    o.y = pack_bf16(asf(v[L][4 + 2 * h]), asf(v[L][5 + 2 * h]));
+                    o.z = pack_bf16(asf(v[L][8 + 2 * h]), asf(v[L][9 + 2 * h]));
+                    o.w = pack_bf16(asf(v[L][12 + 2 * h]), asf(v[L][13 + 2 * h]));
+                    if (row < g.M) *reinterpret_cast<uint4*>(out + (long long)row * g.ldc + col0 + 8 * q) = o;
+                }
+        }
+    } else if constexpr (EPI == CTC_EPI_F32) {
+        // 8 consecutive fp32 channels per thread and row: one 256-bit load of the residual, one 256-bit store; the four
+        // threads of a row cover a full 128-byte line
+        float* out = reinterpret_cast<float*>(g.out);
+#pragma unroll 1
+        for (int c = cbeg; c < cend; c += 32) {
+            const int col0 = colbase + c;
+            if (col0 >= g.N) break;
+            uint32_t res[4][8];
+            if (g.resid) {      // in flight while the accumulator chunk is read
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = row0 + 8 * i + r4;
+                    if (row < g.M) ldg256(g.resid + (long long)row * g.ldr + col0 + 8 * q, res[i]);
+                }
+            }
+            uint32_t bb[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bb[k] = 0u;
+            if (g.bias) ldg256(g.bias + col0 + 8 * q, bb);
+            uint32_t v[2][16];
+            tmem_ld_16x256b_x4(taddr + c, v[0]);
+            tmem_ld_16x256b_x4(taddr + (16u << 16) + c, v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = 2 * L + h;
+                    const int row = row0 + 8 * i + r4;
+                    if (row >= g.M) continue;
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        o[2 * j] = asf(v[L][4 * j + 2 * h]) + asf(bb[2 * j]);
+                        o[2 * j + 1] = asf(v[L][4 * j + 2 * h + 1]) + asf(bb[2 * j + 1]);
+                    }
+                    if (g.resid) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] += asf(res[i][k]);
+                    }
+                    stg256(out + (long long)row * g.ldc + col0 + 8 * q, __float_as_uint(o[0]), __float_as_uint(o[1]),
+                           __float_as_uint(o[2]), __float_as_uint(o[3]), __float_as_uint(o[4]), __float_as_uint(o[5]),
+                           __float_as_uint(o[6]), __float_as_uint(o[7]));
+                }
+        }
+    } else if constexpr (EPI == CTC_EPI_GEGLU) {
+        __nv_bfloat16* hout = reinterpret_cast<__nv_bfloat16*>(g.out);
+        __nv_bfloat16* uout = reinterpret_cast<__nv_bfloat16*>(g.aux);
+#pragma unroll 1
+        for (int c = cbeg; c < cend; c += 64) {
+            const int col0 = colbase + c;
+            if (col0 >= g.N) break;
+#pragma unroll
+            for (int L = 0; L < 2; ++L) {       // 16 rows at a time: bounded live state (16 epilogue warps: 96 registers)
+                uint32_t xv[16], gv[16];
+                tmem_ld_16x256b_x4(taddr + (uint32_t(16 * L) << 16) + c, xv);
+                tmem_ld_16x256b_x4(taddr + (uint32_t(16 * L) << 16) + c + 32, gv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = row0 + 16 * L + 8 * h + r4;
+                    uint32_t hk[4], pa[4], pb[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float x0 = asf(xv[4 * j + 2 * h]), x1 = asf(xv[4 * j + 2 * h + 1]);
+                        const float g0 = asf(gv[4 * j + 2 * h]), g1 = asf(gv[4 * j + 2 * h + 1]);
+                        float c0, p0, c1, p1;
+                        gelu_parts_fast(g0, c0, p0);
+                        gelu_parts_fast(g1, c1, p1);
+                        const float a0 = g0 * c0, a1 = g1 * c1;
+                        hk[j] = pack_bf16(a0 * x0, a1 * x1);
+                        if (uout) {
+                            pa[j] = pack_bf16_alu(a0, a1);
+                            pb[j] = pack_bf16_alu(x0 * fmaf(g0, p0, c0), x1 * fmaf(g1, p1, c1));
+                        }
+                    }
+                    if (row < g.M) {
+                        *reinterpret_cast<uint4*>(hout + (long long)row * g.ldc + col0 / 2 + 8 * q) = make_uint4(hk[0], hk[1], hk[2], hk[3]);
+                        if (uout) {
+                            __nv_bfloat16* pu = uout + (long long)row * g.ldaux + col0 + 8 * q;
+                            *reinterpret_cast<uint4*>(pu) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+                            *reinterpret_cast<uint4*>(pu + 32) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+                        }
+                    }
+                }
+            }
+        }
+    } else if constexpr (EPI == CTC_EPI_GEGLU_BWD) {
+        const __nv_bfloat16* uin = reinterpret_cast<const __nv_bfloat16*>(g.aux);
+        __nv_bfloat16* duout = reinterpret_cast<__nv_bfloat16*>(g.out);
+#pragma unroll 1
+        for (int c = cbeg; c < cend; c += 32) {
+            const int col0 = colbase + c;
+            if (col0 >= g.N) break;
+            uint4 fa[4], fb[4];     // the saved factors of this thread's 4 rows x 8 channels: in flight during the TMEM read
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = row0 + 8 * i + r4;
+                const __nv_bfloat16* pu = uin + (long long)row * g.ldaux + 2 * col0 + 8 * q;
+                const bool ok = row < g.M;
+                fa[i] = ok ? *reinterpret_cast<const uint4*>(pu) : make_uint4(0, 0, 0, 0);
+                fb[i] = ok ? *reinterpret_cast<const uint4*>(pu + 32) : make_uint4(0, 0, 0, 0);
+            }
+            uint32_t v[2][16];
+            tmem_ld_16x256b_x4(taddr + c, v[0]);
+            tmem_ld_16x256b_x4(taddr + (16u << 16) + c, v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = 2 * L + h;
+                    const int row = row0 + 8 * i + r4;
+                    const uint32_t as[4] = {fa[i].x, fa[i].y, fa[i].z, fa[i].w}, bs[4] = {fb[i].x, fb[i].y, fb[i].z, fb[i].w};
+                    uint32_t dv[4], dg[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 af = unpack_bf16(as[j]), bf = unpack_bf16(bs[j]);
+                        const float d0 = asf(v[L][4 * j + 2 * h]), d1 = asf(v[L][4 * j + 2 * h + 1]);
+                        dv[j] = pack_bf16(af.x * d0, af.y * d1);
+                        dg[j] = pack_bf16(bf.x * d0, bf.y * d1);
+                    }
+                    if (row < g.M) {
+                        __nv_bfloat16* pd = duout + (long long)row * g.ldc + 2 * col0 + 8 * q;
+                        *reinterpret_cast<uint4*>(pd) = make_uint4(dv[0], dv[1], dv[2], dv[3]);
+                        *reinterpret_cast<uint4*>(pd + 32) = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+                    }
+                }
+        }
+    }
 }
 
 // running top-2 (value, column) over a row, used by the VQ nearest-code search
@@ -249,11 +465,11 @@ struct Top2 {
     }
 };
 
-template <int BN, int EPI, int CG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int EPI, int CG, int EW, int DS>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmArgs g) {
-    using S = GemmSmem<BN, CG>;
+    using S = GemmSmem<BN, CG, EW, DS>;
     constexpr int kStages = S::kStages;
     constexpr int TM = BM * CG;                                   // rows of one tile (pair mode: 256)
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
@@ -281,7 +497,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * CG); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EW * CG); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -359,7 +575,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ================= epilogue =================
         const int ew = (warp - 4) & 3;   // TMEM lane quarter: warp (id % 4) may only touch lanes 32*(id%4)..+31
         const int eh = (warp - 4) >> 2;  // which half of the tile's columns this warp owns
-        constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+        constexpr int kColsPerWarp = BN / (EW / 4);
         const int cbeg = eh * kColsPerWarp, cend = cbeg + kColsPerWarp;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = unit; tile < num_tiles; tile += n_units) {
@@ -390,8 +606,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         if (pcol + c < 2 * g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + c));
                 }
             }
-            uint4 ureg[EPI == CTC_EPI_GEGLU_BWD ? 8 : 1];
-            if constexpr (EPI == CTC_EPI_GEGLU_BWD) {
+            uint4 ureg[(EPI == CTC_EPI_GEGLU_BWD && DS == 0) ? 8 : 1];
+            if constexpr (EPI == CTC_EPI_GEGLU_BWD && DS == 0) {
                 // first chunk of the saved adjoint factors: in registers before the accumulator is even complete
                 if (tn * BN + cbeg < g.N)
                     stage_load_issue(g, rbase + ew * 32, 2 * (tn * BN + cbeg), lane,
@@ -401,9 +617,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tcgen05_fence_after();
             const int row = rbase + ew * 32 + lane;
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
-            uint8_t* stage = smem + S::kOutOffset + (warp - 4) * 4096;
+            const uint32_t stage = smem_u32(smem + S::kOutOffset + (warp - 4) * S::kStageWarp);
             const int row0 = rbase + ew * 32;
-            if constexpr (EPI == CTC_EPI_ARGMAX) {
+            if constexpr (DS == 1) {
+                epilogue_direct<EPI>(g, taddr, row0, tn * BN, cbeg, cend, lane);
+            } else if constexpr (EPI == CTC_EPI_ARGMAX) {
                 // four independent trackers break the 256-long dependent compare chain
                 Top2 t2[4];
 #pragma unroll
@@ -436,7 +654,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int i = 1; i < 4; ++i) { t2[0].push(t2[i].v0, t2[i].i0); t2[0].push(t2[i].v1, t2[i].i1); }
                 if (row < g.M) {
-                    const long long o = (((long long)row * g.n_tiles_n + tn) * (kEpiWarps / 4) + eh) * 2;
+                    const long long o = (((long long)row * g.n_tiles_n + tn) * (EW / 4) + eh) * 2;
                     g.top2_val[o] = t2[0].v0; g.top2_val[o + 1] = t2[0].v1;
                     g.top2_idx[o] = t2[0].i0; g.top2_idx[o + 1] = t2[0].i1;
                 }
@@ -449,6 +667,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // dh GEMM's epilogue (EPI_GEGLU_BWD) instead of a stand-alone HBM pass over u, dh and du.
                 __nv_bfloat16* hout = reinterpret_cast<__nv_bfloat16*>(g.out);
                 __nv_bfloat16* uout = reinterpret_cast<__nv_bfloat16*>(g.aux);
+                if constexpr (EW == 16) {
+                    // 16 epilogue warps (ncu on the 8-warp version: 0.44 IPC per scheduler, XU pipe 23 %, tensor pipe 45 %:
+                    // two resident warps per scheduler cannot hide the MUFU / TMEM / staging latencies of this epilogue).
+                    // Each warp owns ONE 64-column group of the tile and walks it in two half passes of 16 (value, gate)
+                    // pairs, which keeps the live state under the 96 registers a 640-thread CTA leaves per thread.
+                    static_assert(EW != 16 || BN == 256, "16 epilogue warps: one [32 value | 32 gate] group per warp");
+                    const int col0 = tn * BN + cbeg;
+                    if (col0 < g.N) {
+                        const int un = lane & 3;
+                        uint32_t hk[16];
+#pragma unroll
+                        for (int hp = 0; hp < 2; ++hp) {
+                            uint32_t xv[16], gv[16], pk[16];
+                            tmem_ld_32x32b_x16(taddr + cbeg + hp * 16, xv);
+                            tmem_ld_32x32b_x16(taddr + cbeg + 32 + hp * 16, gv);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float x0 = __uint_as_float(xv[2 * j]), x1 = __uint_as_float(xv[2 * j + 1]);
+                                const float g0 = __uint_as_float(gv[2 * j]), g1 = __uint_as_float(gv[2 * j + 1]);
+                                float c0, p0, c1, p1;
+                                gelu_parts_fast(g0, c0, p0);
+                                gelu_parts_fast(g1, c1, p1);
+                                const float a0 = g0 * c0, a1 = g1 * c1;
+                                hk[hp * 8 + j] = pack_bf16(a0 * x0, a1 * x1);
+                                pk[j] = pack_bf16_alu(a0, a1);
+                                pk[8 + j] = pack_bf16_alu(x0 * fmaf(g0, p0, c0), x1 * fmaf(g1, p1, c1));
+                            }
+                            // units 0, 1 of a staged row = a (16 columns), units 2, 3 = b: 32 columns further in [a | b]
+                            if (uout) staged64_store(g, stage, row0, lane, pk, uout, g.ldaux, col0 + hp * 16 + (un & 1) * 8 + (un >> 1) * 32);
+                        }
+                        staged64_store(g, stage, row0, lane, hk, hout, g.ldc, col0 / 2 + un * 8);
+                    }
+                } else
 #pragma unroll 1
                 for (int c = cbeg; c < cend; c += 64) {
                     const int col0 = tn * BN + c;
@@ -501,8 +753,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     uint4 aa4[4], ba4[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        aa4[u] = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u));
-                        ba4[u] = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u + 4));
+                        aa4[u] = lds128(stage + stage_off(lane, u));
+                        ba4[u] = lds128(stage + stage_off(lane, u + 4));
                     }
                     // next chunk's factors on their way while this one is multiplied and stored
                     if (c + 32 < cend && col0 + 32 < g.N) stage_load_issue(g, row0, 2 * (col0 + 32), lane, uin, g.ldaux, ureg);
@@ -595,10 +847,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, long long lda,
-                                 const __nv_bfloat16* __restrict__ B, long long ldb, const GemmArgs g) {
+                                 const __nv_bfloat16* __restrict__ B, long long ldb, const GemmArgs g, int perm_kind) {
     __shared__ float sa[16][17], sb[16][17];
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+    const int row = blockIdx.y * 16 + ty;
+    int col = blockIdx.x * 16 + tx;
     float acc = 0.f;
     for (int k0 = 0; k0 < g.K; k0 += 16) {
         const int ka = k0 + tx;
@@ -611,6 +864,10 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, long long 
         __syncthreads();
     }
     if (row >= g.M || col >= g.N) return;
+    // B rows permuted for the direct epilogues: row (col) of B holds the weights of output channel row_perm(col)
+    const int col_b = col;
+    (void)col_b;
+    if (perm_kind) col = (col & ~31) + row_perm(col & 31);
     if constexpr (EPI == CTC_EPI_BF16) {
         reinterpret_cast<__nv_bfloat16*>(g.out)[(long long)row * g.ldc + col] = __float2bfloat16(acc);
     } else {
@@ -667,13 +924,14 @@ int num_sms() {
     return g_num_sms[dev];
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int EW = kEpiWarps, int DS = 0>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
-    using S = GemmSmem<BN, CG>;
+    using S = GemmSmem<BN, CG, EW, DS>;
+    constexpr int kGemmThreads = 128 + 32 * EW;
     static bool configured_dev[kMaxDevices] = {};
     bool& configured = configured_dev[current_device()];
     if (!configured) {
-        CTC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CTC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG, EW, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             S::kTotal));
         configured = true;
     }
@@ -687,9 +945,9 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArg
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        CTC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, ta, tb, g));
+        CTC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG, EW, DS>, ta, tb, g));
     } else {
-        gemm_tcgen05_kernel<BN, EPI, CG><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, g);
+        gemm_tcgen05_kernel<BN, EPI, CG, EW, DS><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, g);
     }
     CTC_LAUNCH_CHECK();
     return 0;
@@ -699,6 +957,17 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
               int K, int epi, const float* bias, const float* resid, long long ldr, void* aux, long long ldaux,
               float* top2_val, int* top2_idx, int impl, cudaStream_t st) {
     CTC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    // B rows permuted inside every 32-row group (ctc_gemm_row_perm) -> the staging-free direct epilogue
+    const int perm_kind = (impl & CTC_GEMM_BPERM) ? 1 : 0;
+    impl &= 0xff;
+    if (perm_kind) {
+        CTC_REQUIRE(epi != CTC_EPI_ARGMAX && N % 32 == 0, "gemm: permuted B rows need N %% 32 == 0 (N=%d) and a storing epilogue", N);
+        const bool f32 = epi == CTC_EPI_F32;   // fp32 rows move as 256-bit accesses
+        CTC_REQUIRE(ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & (f32 ? 31 : 15)) == 0 &&
+                    (!resid || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(resid) & 31) == 0)) &&
+                    (!bias || (reinterpret_cast<uintptr_t>(bias) & 31) == 0),
+                    "gemm: the direct epilogue needs %d-byte aligned rows (ldc=%lld)", f32 ? 32 : 16, ldc);
+    }
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.out = out; g.ldc = ldc; g.bias = bias; g.resid = resid; g.ldr = ldr;
     g.top2_val = top2_val; g.top2_idx = top2_idx; g.aux = aux; g.ldaux = ldaux;
@@ -714,10 +983,10 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
         dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
         if (epi == CTC_EPI_BF16)
             gemm_simt_kernel<CTC_EPI_BF16><<<grid, block, 0, st>>>((const __nv_bfloat16*)A, lda,
-                                                                   (const __nv_bfloat16*)B, ldb, g);
+                                                                   (const __nv_bfloat16*)B, ldb, g, perm_kind);
         else
             gemm_simt_kernel<CTC_EPI_F32><<<grid, block, 0, st>>>((const __nv_bfloat16*)A, lda,
-                                                                  (const __nv_bfloat16*)B, ldb, g);
+                                                                  (const __nv_bfloat16*)B, ldb, g, perm_kind);
         CTC_LAUNCH_CHECK();
         return 0;
     }
@@ -734,20 +1003,34 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
     // narrow to_q / to_out launches and under the arithmetic-heavy GEGLU epilogue, where the leader's MMA issue has to
     // wait for the slower of two epilogues; impl = CTC_GEMM_TCGEN05_PAIR forces pairs everywhere (tests).
     // The VQ score GEMM (N = 8192, K = 512, top-2 epilogue) also prefers single CTAs: 749 us in pairs vs 652 us.
+    static const int geglu_pair_env = [] { const char* e = getenv("CTC_GEMM_GEGLU_PAIR"); return e ? atoi(e) : 0; }();
     const bool want_pair = impl == CTC_GEMM_TCGEN05_PAIR ||
-                           (pair_env && K >= 512 && N >= 512 && epi != CTC_EPI_GEGLU && epi != CTC_EPI_ARGMAX);
+                           (pair_env && K >= 512 && N >= 512 && epi != CTC_EPI_ARGMAX &&
+                            (epi != CTC_EPI_GEGLU || (perm_kind && geglu_pair_env)));
     const bool pair = bn256 && impl != CTC_GEMM_TCGEN05_1CTA && want_pair && (num_sms() % 2 == 0);
+    // 16 epilogue warps for the GEGLU epilogue (CTC_GEMM_EW16=0 switches back to 8: an A/B measurement aid)
+    static const int ew16_env = [] { const char* e = getenv("CTC_GEMM_EW16"); return e ? atoi(e) : 1; }();
     g.n_tiles_n = (N + BNsel - 1) / BNsel;
     CUtensorMap ta, tb;
     if (int e = make_tmap_bf16(&ta, A, M, K, lda, BM)) return e;
     if (int e = make_tmap_bf16(&tb, B, N, K, ldb, pair ? BNsel / 2 : BNsel)) return e;
 #define CTC_GEMM_DISPATCH(EPI)                                                                                   \
+    if (perm_kind)                                                                                               \
+        return pair ? launch_tc<256, EPI, 2, kEpiWarps, 1>(ta, tb, g, st)                                        \
+                    : (bn256 ? launch_tc<256, EPI, 1, kEpiWarps, 1>(ta, tb, g, st)                               \
+                             : launch_tc<128, EPI, 1, kEpiWarps, 1>(ta, tb, g, st));                             \
     return pair ? launch_tc<256, EPI, 2>(ta, tb, g, st)                                                          \
                 : (bn256 ? launch_tc<256, EPI, 1>(ta, tb, g, st) : launch_tc<128, EPI, 1>(ta, tb, g, st))
     switch (epi) {
         case CTC_EPI_BF16: CTC_GEMM_DISPATCH(CTC_EPI_BF16);
         case CTC_EPI_F32: CTC_GEMM_DISPATCH(CTC_EPI_F32);
-        case CTC_EPI_GEGLU: CTC_GEMM_DISPATCH(CTC_EPI_GEGLU);
+        case CTC_EPI_GEGLU:
+            if (bn256 && ew16_env) {
+                if (perm_kind) return pair ? launch_tc<256, CTC_EPI_GEGLU, 2, 16, 1>(ta, tb, g, st)
+                                           : launch_tc<256, CTC_EPI_GEGLU, 1, 16, 1>(ta, tb, g, st);
+                if (!pair) return launch_tc<256, CTC_EPI_GEGLU, 1, 16>(ta, tb, g, st);
+            }
+            CTC_GEMM_DISPATCH(CTC_EPI_GEGLU);
         case CTC_EPI_GEGLU_BWD: CTC_GEMM_DISPATCH(CTC_EPI_GEGLU_BWD);
         case CTC_EPI_ARGMAX:
             CTC_REQUIRE(top2_val && top2_idx, "gemm: arg-max epilogue needs top2 buffers");
@@ -756,6 +1039,12 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
             CTC_REQUIRE(false, "gemm: unknown epilogue %d", epi);
     }
 #undef CTC_GEMM_DISPATCH
+    return 0;
+}
+
+// perm[a] = output channel (within its 32-channel group) held by accumulator column a: B row (G*32 + a) := W[G*32 + perm[a]]
+int gemm_row_perm(int* perm32) {
+    for (int a = 0; a < 32; ++a) perm32[a] = row_perm(a);
     return 0;
 }
 

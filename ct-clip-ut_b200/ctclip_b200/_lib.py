@@ -22,6 +22,7 @@ P, I, L, F = c_void_p, c_int, c_int64, c_float
 SIGNATURES = {
     "ctc_device_check": [],
     "ctc_gemm_bf16": [P, L, P, L, P, L, I, I, I, I, P, P, L, P, L, I, P],
+    "ctc_gemm_row_perm": [P],
     "ctc_patchify_ln_fwd": [P, L, I, I, I, I, I, I, P, P, F, P, P, F, P, P],
     "ctc_patchify_ln_bwd": [P, L, I, I, I, I, I, I, P, F, P, P, P, I, F, P],
     "ctc_layernorm_fwd": [P, I, I, P, P, F, P, P, P, P],
@@ -78,6 +79,15 @@ OTHER_SYMBOLS = {"ctc_version": (c_int, []), "ctc_last_error": (c_char_p, []),
 
 EPI_BF16, EPI_F32, EPI_ARGMAX, EPI_GEGLU, EPI_GEGLU_BWD = 0, 1, 2, 3, 4
 GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_1CTA, GEMM_TCGEN05_PAIR = 0, 1, 2, 3
+GEMM_BPERM = 0x100   # flag OR-ed into impl: B rows permuted (gemm_row_perm) for the staging-free direct epilogues
+
+
+def gemm_row_perm():
+    """perm[a] = output channel (inside its group of 32) whose weights go to row a of that group of B."""
+    arr = (c_int * 32)()
+    if load().ctc_gemm_row_perm(arr) != 0:
+        raise RuntimeError(load().ctc_last_error().decode())
+    return list(arr)
 MODE_SPATIAL, MODE_TEMPORAL = 0, 1
 
 _lib = None

@@ -151,7 +151,7 @@ class Engine:
         assert w.shape[1] == K and out.shape[0] == M
         call("ctc_gemm_bf16", a, a.stride(0), w, w.stride(0), out, out.stride(0), M, N, K, epi, bias, resid,
              resid.stride(0) if resid is not None else 0, aux, aux.stride(0) if aux is not None else 0,
-             self.gemm_impl, stream_ptr())
+             self.gemm_impl | self.plan.gemm_flags.get(w.data_ptr(), 0), stream_ptr())
         return out
 
     def layernorm(self, x, g, b, y_bf16=None, y_f32=None, xraw=None):

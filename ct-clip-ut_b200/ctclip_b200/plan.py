@@ -8,6 +8,8 @@ re-evaluates for all 576² pairs on every forward (attention.py:259-277) — is 
 """
 from __future__ import annotations
 
+import os
+
 import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
@@ -67,8 +69,25 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
 class Plan:
     """Device-resident, kernel-ready weights."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Config, device: Optional[torch.device] = None):
+    def _pack(self, w: torch.Tensor) -> torch.Tensor:
+        """bf16 B operand [N, K] of a GEMM.  When N is a multiple of 32 its rows are permuted inside every group of 32
+        (ctc_gemm_row_perm) and the tensor is registered in `gemm_flags`, so that Engine.gemm selects the staging-free
+        direct epilogue for it; the result of the GEMM is the same either way."""
+        t = _bf16(w)
+        if t.shape[0] % 32 == 0 and self.direct_epilogue:
+            if self._perm is None:
+                self._perm = torch.tensor(_lib.gemm_row_perm(), device=t.device, dtype=torch.long)
+            t = t.view(t.shape[0] // 32, 32, t.shape[1])[:, self._perm, :].reshape(t.shape).contiguous()
+            self.gemm_flags[t.data_ptr()] = _lib.GEMM_BPERM
+        return t
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: Config, device: Optional[torch.device] = None,
+                 direct_epilogue: Optional[bool] = None):
         _lib.require_device()
+        # CTC_GEMM_DIRECT=0: keep the weights unpermuted and use the staged GEMM epilogues (A/B measurement aid)
+        self.direct_epilogue = (os.environ.get("CTC_GEMM_DIRECT", "1") != "0") if direct_epilogue is None else direct_epilogue
+        self.gemm_flags: Dict[int, int] = {}
+        self._perm: Optional[torch.Tensor] = None
         if cfg.dim_head != 32:
             raise RuntimeError("ctclip_b200: the attention kernels are specialised for dim_head == 32 "
                                "(src/inference_ctclip.py:29)")
@@ -83,7 +102,7 @@ class Plan:
         # patch embedding (ctvit.py:44-52)
         self.pe_ln1_w, self.pe_ln1_b = f32(vt + "to_patch_emb.1.weight"), f32(vt + "to_patch_emb.1.bias")
         w = f32(vt + "to_patch_emb.2.weight")                      # [C, P]
-        self.pe_w, self.pe_w_t = _bf16(w), _bf16(w.t())
+        self.pe_w, self.pe_w_t = self._pack(w), self._pack(w.t())
         self.pe_b = f32(vt + "to_patch_emb.2.bias")
         self.pe_ln2_w, self.pe_ln2_b = f32(vt + "to_patch_emb.3.weight"), f32(vt + "to_patch_emb.3.bias")
 
@@ -131,8 +150,8 @@ class Plan:
         lw.ln_g, lw.ln_b = f32("1.norm.gamma"), f32("1.norm.beta")
         lw.q_scale, lw.k_scale = f32("1.q_scale"), f32("1.k_scale")
         wq, wkv, wout = f32("1.to_q.weight"), f32("1.to_kv.weight"), f32("1.to_out.weight")
-        lw.wq, lw.wkv, lw.wout = _bf16(wq), _bf16(wkv), _bf16(wout)
-        lw.wq_t, lw.wkv_t, lw.wout_t = _bf16(wq.t()), _bf16(wkv.t()), _bf16(wout.t())
+        lw.wq, lw.wkv, lw.wout = self._pack(wq), self._pack(wkv), self._pack(wout)
+        lw.wq_t, lw.wkv_t, lw.wout_t = self._pack(wq.t()), self._pack(wkv.t()), self._pack(wout.t())
         lw.ff_ln_w, lw.ff_ln_b = f32("3.0.weight"), f32("3.0.bias")
         w1, w2 = f32("3.1.weight"), f32("3.4.weight")                          # [2F, C], [C, F]
         # GEGLU halves (attention.py:40: x, gate = chunk(2)), zero-padded to FP and interleaved in 64-row groups
@@ -143,6 +162,6 @@ class Plan:
         w1p = torch.stack([val.view(FP // 32, 32, C), gate.view(FP // 32, 32, C)], dim=1).reshape(2 * FP, C)
         w2p = torch.zeros(C, FP, device=w2.device)
         w2p[:, :F] = w2
-        lw.w1, lw.w2 = _bf16(w1p), _bf16(w2p)
-        lw.w1_t, lw.w2_t = _bf16(w1p.t()), _bf16(w2p.t())
+        lw.w1, lw.w2 = self._pack(w1p), self._pack(w2p)
+        lw.w1_t, lw.w2_t = self._pack(w1p.t()), self._pack(w2p.t())
         return lw

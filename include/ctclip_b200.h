@@ -34,6 +34,11 @@ enum { CTC_EPI_BF16 = 0, CTC_EPI_F32 = 1, CTC_EPI_ARGMAX = 2, CTC_EPI_GEGLU = 3,
  * faster, single CTAs otherwise); TCGEN05_1CTA / TCGEN05_PAIR force one kernel and SIMT is a plain comparator -
  * all three for tests and A/B measurements. */
 enum { CTC_GEMM_TCGEN05 = 0, CTC_GEMM_SIMT = 1, CTC_GEMM_TCGEN05_1CTA = 2, CTC_GEMM_TCGEN05_PAIR = 3 };
+/* Flag OR-ed into `impl`: the rows of B (= output channels) have been permuted inside every 32-row group with
+ * ctc_gemm_row_perm when the weight was packed, which lets the epilogue store straight from the tcgen05.ld.16x256b
+ * register layout without a shared-memory staging pass.  Results are bit-identical to the
+ * unflagged call on the unpermuted B.  N must be a multiple of 32; fp32 outputs / residual / bias 32-byte aligned. */
+enum { CTC_GEMM_BPERM = 0x100 };
 /* sequence mode of the factorised transformer (ctvit.py:94-101) */
 enum { CTC_MODE_SPATIAL = 0, CTC_MODE_TEMPORAL = 1 };
 
@@ -56,6 +61,9 @@ long long ctc_launch_count(void);
 int ctc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldc, int M, int N,
                   int K, int epi, const float* bias, const float* resid, int64_t ldr, void* aux, int64_t ldaux,
                   int impl, void* stream);
+/* perm32[a] (host, 32 ints) = the output channel, within its group of 32, whose weights belong in row a of that
+ * group of B for CTC_GEMM_BPERM: Bperm[G*32 + a] = B[G*32 + perm32[a]]. */
+int ctc_gemm_row_perm(int* perm32);
 
 /* 3-D patchify + LayerNorm(P) (ctvit.py:44-49): volume fp32 [B,1,D,H,W] -> bf16 [B*T*H*W, P]
  * (P = pt*p*p, element order pt,p1,p2).  Fused on load, so perturbed volumes are never

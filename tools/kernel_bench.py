@@ -31,7 +31,7 @@ def rnd(*shape, dtype=torch.float32, scale=1.0):
 
 if what in ("gemm", "all"):
     for name, N, K, epi, resid in [("q", 256, 512, L.EPI_BF16, False), ("kv", 512, 512, L.EPI_BF16, False),
-                                   ("out+res", 512, 256, L.EPI_F32, True), ("ff1 geglu (no u)", 2816, 512, L.EPI_GEGLU, False),
+                                   ("out+res", 512, 256, L.EPI_F32, True), ("ff1 geglu (no u)", 2816, 512, L.EPI_GEGLU, False), ("ff1 geglu + factors", 2816, 512, L.EPI_GEGLU, "u"),
                                    ("ff2+res", 512, 1408, L.EPI_F32, True), ("dh", 1408, 512, L.EPI_BF16, False), ("dh + geglu adjoint", 1408, 512, L.EPI_GEGLU_BWD, False),
                                    ("dxn2", 512, 2816, L.EPI_F32, False), ("pe", 512, 4000, L.EPI_F32, False),
                                    ("pe bwd", 4000, 512, L.EPI_BF16, False)]:
@@ -43,6 +43,8 @@ if what in ("gemm", "all"):
             aux = rnd(R, 2 * N, dtype=bf)
         elif epi == L.EPI_GEGLU:
             out = torch.empty(R, N // 2, device=dev, dtype=bf)
+            if resid == "u":
+                aux, resid = torch.empty(R, N, device=dev, dtype=bf), False
         else:
             out = torch.empty(R, N, device=dev, dtype=bf if epi == L.EPI_BF16 else torch.float32)
         res = rnd(R, N) if resid else None
@@ -51,10 +53,13 @@ if what in ("gemm", "all"):
                    aux.stride(0) if aux is not None else 0, impl, L.stream_ptr())
         us = timeit(lambda: f(3))            # CTA pairs (cta_group::2)
         us1 = timeit(lambda: f(2))           # single-CTA kernel (cta_group::1)
+        # direct (staging-free) epilogues: timing only - the weight rows are not permuted here, the work is identical
+        flag = L.GEMM_BPERM
+        usd, usd1 = timeit(lambda: f(3 | flag)), timeit(lambda: f(2 | flag))
         usb = timeit(lambda: torch.matmul(a, w.t()))     # cuBLAS, bare bf16 GEMM (no epilogue work)
         fl = 2.0 * R * N * K / 1e6
-        print(f"  gemm {name:18s} N={N:5d} K={K:5d}: pair {us:8.1f} us {fl / us:7.1f} TF | 1cta {us1:8.1f} us {fl / us1:7.1f} TF"
-              f" | cuBLAS {usb:8.1f} us {fl / usb:7.1f} TF")
+        print(f"  gemm {name:20s} N={N:5d} K={K:5d}: staged pair {us:6.1f} 1cta {us1:6.1f} | direct pair {usd:6.1f} us {fl / usd:6.0f} TF"
+              f"  1cta {usd1:6.1f} us {fl / usd1:6.0f} TF | cuBLAS {usb:6.1f} us {fl / usb:6.0f} TF")
 
 for mode, tag in ((1, "attn_t"), (0, "attn_s")):
     if what not in (tag, "all"):
