@@ -80,20 +80,41 @@ CTC_DEVINL void gelu_parts(float x, float& cdf, float& pdf) {
     cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
     pdf = 0.3989422804014327f * e;
 }
-// The same with the raw approximate instructions (MUFU.RCP / MUFU.EX2, flush-to-zero, no range-scaling wrappers) for
-// the GEMM epilogues, where the GEGLU arithmetic - not the tensor core - paces the tile (ncu: 37.7 % tensor-pipe
-// active, 31 instructions and 3.5 XU-pipe operations per element before this version).  14 instructions, 2 XU ops.
-CTC_DEVINL void gelu_parts_fast(float x, float& cdf, float& pdf) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    float t, e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
-                                0.254829592f);
-    const float erf_abs = fmaf(-poly, e, 1.0f);
-    cdf = fmaf(copysignf(erf_abs, x), 0.5f, 0.5f);
-    pdf = 0.3989422804014327f * e;
+// GEGLU of two adjacent (value, gate) pairs for the GEMM epilogues, where this arithmetic - not the tensor core - paces
+// the tile: raw approximate instructions (MUFU.RCP / MUFU.EX2, flush-to-zero, no range-scaling wrappers) and PACKED fp32
+// arithmetic (fma / mul .f32x2 -> FFMA2 / FMUL2: one issue slot for both pairs).  Abramowitz-Stegun 7.1.26 with the
+// polynomial negated (pn = -poly):  erf|g/sqrt2| = 1 + pn * exp(-g^2/2),  cdf = 0.5 + 0.5 * sign(g) * erf,
+//   a = gelu(g) = g * cdf,   h = a * x,   b = x * gelu'(g) = x * (cdf + g * pdf),   pdf = exp(-g^2/2) / sqrt(2 pi).
+// 12 issue slots per pair with the adjoint factors (22 with scalar instructions), 8 without.  Every lane operation is a
+// correctly rounded fma / mul, so the result does not depend on how pairs are grouped into packed instructions.
+struct F2 { unsigned long long v; };
+CTC_DEVINL F2 f2_pack(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+CTC_DEVINL void f2_unpack(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+CTC_DEVINL F2 f2_fma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+CTC_DEVINL F2 f2_mul(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+CTC_DEVINL F2 f2_c(float c) { return f2_pack(c, c); }
+template <bool FACTORS>
+CTC_DEVINL void geglu_pair2(float x0, float x1, float g0, float g1, F2& h, F2& a, F2& b) {
+    float t0, t1, e0, e1, w0, w1, r0, r1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(__fmaf_rn(fabsf(g0), 0.23164189f, 1.0f)));    // 0.3275911 / sqrt(2)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(__fmaf_rn(fabsf(g1), 0.23164189f, 1.0f)));
+    const F2 G = f2_pack(g0, g1), X = f2_pack(x0, x1), T = f2_pack(t0, t1);
+    f2_unpack(f2_mul(f2_mul(G, f2_c(-0.72134752f)), G), w0, w1);                                      // -g^2/2 * log2(e)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w1));
+    const F2 E = f2_pack(e0, e1);
+    F2 P = f2_fma(T, f2_c(-1.061405429f), f2_c(1.453152027f));
+    P = f2_fma(P, T, f2_c(-1.421413741f));
+    P = f2_fma(P, T, f2_c(0.284496736f));
+    P = f2_fma(P, T, f2_c(-0.254829592f));
+    P = f2_mul(P, T);
+    f2_unpack(f2_fma(P, E, f2_c(1.0f)), r0, r1);
+    const F2 C = f2_fma(f2_pack(copysignf(r0, g0), copysignf(r1, g1)), f2_c(0.5f), f2_c(0.5f));
+    a = f2_mul(G, C);
+    h = f2_mul(a, X);
+    if constexpr (FACTORS) b = f2_mul(X, f2_fma(f2_mul(G, E), f2_c(0.3989422804f), C));
 }
+CTC_DEVINL uint32_t f2_pack_bf16(F2 v) { float lo, hi; f2_unpack(v, lo, hi); return pack_bf16(lo, hi); }
 // bf16x2 pack on the integer pipe (round half away from zero: +0x8000 on the bit pattern, keep the high halves): the
 // F2FP conversion shares the 16-lane XU pipe with MUFU, which the GEGLU epilogues saturate
 CTC_DEVINL uint32_t pack_bf16_alu(float lo, float hi) {
@@ -282,8 +303,13 @@ CTC_DEVINL uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
+// Remote arrive on a barrier of the cluster, CTA-scope release (the form CUTLASS uses for its accumulator-empty barrier).
+// The explicit `.release.cluster` this used to carry made ptxas put a MEMBAR.ALL.GPU in front of it: every epilogue warp
+// of a CTA pair then waited, once per tile, until all of its outstanding global STORES had drained (ncu: 0.7 - 1.7
+// membar stalls per issued instruction in the pair kernels) although the barrier only hands a TMEM buffer back to the
+// MMA issuer - and the tcgen05.ld of that buffer have completed (tcgen05.wait::ld) before the arrive is issued.
 CTC_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <uint32_t kCols>
 CTC_DEVINL void tmem_alloc_cg2(uint32_t* smem_dst) {  // one full warp in EACH CTA of the pair

@@ -385,15 +385,15 @@ CTC_DEVINL void epilogue_direct(const GemmArgs& g, uint32_t taddr, int row0, int
                     for (int j = 0; j < 4; ++j) {
                         const float x0 = asf(xv[4 * j + 2 * h]), x1 = asf(xv[4 * j + 2 * h + 1]);
                         const float g0 = asf(gv[4 * j + 2 * h]), g1 = asf(gv[4 * j + 2 * h + 1]);
-                        float c0, p0, c1, p1;
-                        gelu_parts_fast(g0, c0, p0);
-                        gelu_parts_fast(g1, c1, p1);
-                        const float a0 = g0 * c0, a1 = g1 * c1;
-                        hk[j] = pack_bf16(a0 * x0, a1 * x1);
+                        F2 hh, aa, bb;
                         if (uout) {
-                            pa[j] = pack_bf16_alu(a0, a1);
-                            pb[j] = pack_bf16_alu(x0 * fmaf(g0, p0, c0), x1 * fmaf(g1, p1, c1));
+                            geglu_pair2<true>(x0, x1, g0, g1, hh, aa, bb);
+                            pa[j] = f2_pack_bf16(aa);
+                            pb[j] = f2_pack_bf16(bb);
+                        } else {
+                            geglu_pair2<false>(x0, x1, g0, g1, hh, aa, bb);
                         }
+                        hk[j] = f2_pack_bf16(hh);
                     }
                     if (row < g.M) {
                         *reinterpret_cast<uint4*>(hout + (long long)row * g.ldc + col0 / 2 + 8 * q) = make_uint4(hk[0], hk[1], hk[2], hk[3]);
@@ -685,15 +685,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float x0 = __uint_as_float(xv[2 * j]), x1 = __uint_as_float(xv[2 * j + 1]);
-                                const float g0 = __uint_as_float(gv[2 * j]), g1 = __uint_as_float(gv[2 * j + 1]);
-                                float c0, p0, c1, p1;
-                                gelu_parts_fast(g0, c0, p0);
-                                gelu_parts_fast(g1, c1, p1);
-                                const float a0 = g0 * c0, a1 = g1 * c1;
-                                hk[hp * 8 + j] = pack_bf16(a0 * x0, a1 * x1);
-                                pk[j] = pack_bf16_alu(a0, a1);
-                                pk[8 + j] = pack_bf16_alu(x0 * fmaf(g0, p0, c0), x1 * fmaf(g1, p1, c1));
+                                F2 hh, aa, bb;
+                                geglu_pair2<true>(__uint_as_float(xv[2 * j]), __uint_as_float(xv[2 * j + 1]), __uint_as_float(gv[2 * j]),
+                                                  __uint_as_float(gv[2 * j + 1]), hh, aa, bb);
+                                hk[hp * 8 + j] = f2_pack_bf16(hh);
+                                pk[j] = f2_pack_bf16(aa);
+                                pk[8 + j] = f2_pack_bf16(bb);
                             }
                             // units 0, 1 of a staged row = a (16 columns), units 2, 3 = b: 32 columns further in [a | b]
                             if (uout) staged64_store(g, stage, row0, lane, pk, uout, g.ldaux, col0 + hp * 16 + (un & 1) * 8 + (un >> 1) * 32);
@@ -714,26 +711,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         uint32_t pk[32];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float x0 = __uint_as_float(xv[2 * j]), x1 = __uint_as_float(xv[2 * j + 1]);
-                            const float g0 = __uint_as_float(gv[2 * j]), g1 = __uint_as_float(gv[2 * j + 1]);
-                            float c0, p0, c1, p1;
-                            gelu_parts_fast(g0, c0, p0);
-                            gelu_parts_fast(g1, c1, p1);
-                            const float a0 = g0 * c0, a1 = g1 * c1;
-                            hk[j] = pack_bf16(a0 * x0, a1 * x1);
-                            pk[j] = pack_bf16_alu(a0, a1);                     // the saved factors are packed on the ALU pipe
-                            pk[16 + j] = pack_bf16_alu(x0 * fmaf(g0, p0, c0), x1 * fmaf(g1, p1, c1));
+                            F2 hh, aa, bb;
+                            geglu_pair2<true>(__uint_as_float(xv[2 * j]), __uint_as_float(xv[2 * j + 1]), __uint_as_float(gv[2 * j]),
+                                              __uint_as_float(gv[2 * j + 1]), hh, aa, bb);
+                            hk[j] = f2_pack_bf16(hh);
+                            pk[j] = f2_pack_bf16(aa);
+                            pk[16 + j] = f2_pack_bf16(bb);
                         }
                         epilogue_bf16_staged(g, stage, row0, col0, lane, pk, uout, g.ldaux);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             // same arithmetic as the branch above, so that h does not depend on whether u is saved
-                            const float g0 = __uint_as_float(gv[2 * j]), g1 = __uint_as_float(gv[2 * j + 1]);
-                            float c0, p0, c1, p1;
-                            gelu_parts_fast(g0, c0, p0);
-                            gelu_parts_fast(g1, c1, p1);
-                            hk[j] = pack_bf16((g0 * c0) * __uint_as_float(xv[2 * j]), (g1 * c1) * __uint_as_float(xv[2 * j + 1]));
+                            F2 hh, aa, bb;
+                            geglu_pair2<false>(__uint_as_float(xv[2 * j]), __uint_as_float(xv[2 * j + 1]), __uint_as_float(gv[2 * j]),
+                                               __uint_as_float(gv[2 * j + 1]), hh, aa, bb);
+                            hk[j] = f2_pack_bf16(hh);
                         }
                     }
                     epilogue_bf16_staged32(g, stage, row0, col0 / 2, lane, hk, hout, g.ldc);
@@ -998,15 +991,14 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
     // CTA pairs (cta_group::2, 256 x 256 tiles) for every 256-wide case unless the caller asks for the single-CTA kernel
     // (CTC_GEMM_PAIR=0 in the environment switches the default back to single CTAs: an A/B measurement aid)
     static const int pair_env = [] { const char* e = getenv("CTC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
-    // Measured on B200 at M = 110 592 (tools/kernel_bench.py, profiles/r02_gemm_pair_vs_1cta.md): pairs win 3-10 % where both
-    // the reduction and the output are wide (to_kv, FF2, dh, dxn2, patch embedding and its adjoint) and lose 3-6 % on the
-    // narrow to_q / to_out launches and under the arithmetic-heavy GEGLU epilogue, where the leader's MMA issue has to
-    // wait for the slower of two epilogues; impl = CTC_GEMM_TCGEN05_PAIR forces pairs everywhere (tests).
-    // The VQ score GEMM (N = 8192, K = 512, top-2 epilogue) also prefers single CTAs: 749 us in pairs vs 652 us.
-    static const int geglu_pair_env = [] { const char* e = getenv("CTC_GEMM_GEGLU_PAIR"); return e ? atoi(e) : 0; }();
-    const bool want_pair = impl == CTC_GEMM_TCGEN05_PAIR ||
-                           (pair_env && K >= 512 && N >= 512 && epi != CTC_EPI_ARGMAX &&
-                            (epi != CTC_EPI_GEGLU || (perm_kind && geglu_pair_env)));
+    // Measured on B200 at M = 110 592 (tools/kernel_bench.py, profiles/r02_kernel_bench_v3.log).  Until the remote
+    // accumulator-empty arrive lost its GPU-scope fence (mbar_arrive_cluster) pairs only won where K >= 512 and N >= 512
+    // and lost under the GEGLU epilogue; since then they win on every shape of the step: to_q 34.3 -> 32.3 us,
+    // to_kv 60.0 -> 50.5, FF1 + GEGLU 265 -> 255 (+ factors 348 -> 307), dh 153 -> 137, patch embedding 390 -> 326 and its
+    // adjoint 462 -> 347 us (cuBLAS, bare GEMM: 35.9 / 55.2 / 265 / 145 / 315 / 461 us).
+    // impl = CTC_GEMM_TCGEN05_PAIR / _1CTA force either kernel (tests, A/B measurement).
+    static const int argmax_pair_env = [] { const char* e = getenv("CTC_GEMM_ARGMAX_PAIR"); return e ? atoi(e) : 0; }();
+    const bool want_pair = impl == CTC_GEMM_TCGEN05_PAIR || (pair_env && (epi != CTC_EPI_ARGMAX || argmax_pair_env));
     const bool pair = bn256 && impl != CTC_GEMM_TCGEN05_1CTA && want_pair && (num_sms() % 2 == 0);
     // 16 epilogue warps for the GEGLU epilogue (CTC_GEMM_EW16=0 switches back to 8: an A/B measurement aid)
     static const int ew16_env = [] { const char* e = getenv("CTC_GEMM_EW16"); return e ? atoi(e) : 1; }();
@@ -1025,7 +1017,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* 
         case CTC_EPI_BF16: CTC_GEMM_DISPATCH(CTC_EPI_BF16);
         case CTC_EPI_F32: CTC_GEMM_DISPATCH(CTC_EPI_F32);
         case CTC_EPI_GEGLU:
-            if (bn256 && ew16_env) {
+            if (bn256 && ew16_env) {       // 16 epilogue warps (the staged pair kernel keeps 8: 6 stages + 16 x 4 KB do not fit)
                 if (perm_kind) return pair ? launch_tc<256, CTC_EPI_GEGLU, 2, 16, 1>(ta, tb, g, st)
                                            : launch_tc<256, CTC_EPI_GEGLU, 1, 16, 1>(ta, tb, g, st);
                 if (!pair) return launch_tc<256, CTC_EPI_GEGLU, 1, 16>(ta, tb, g, st);

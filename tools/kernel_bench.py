@@ -103,3 +103,15 @@ for mode, tag in ((1, "attn_t"), (0, "attn_s")):
         t_poly = timeit(fwd_tc)
         print(f"  {tag} fwd tcgen05: all exponentials on MUFU {t_mufu:8.1f} us | half on FMA-pipe polynomials {t_poly:8.1f} us "
               f"(score bound {bound:.2f})")
+
+if what in ("vq", "all"):
+    C, K = 512, 8192
+    x = rnd(R, C)
+    xb = x.to(bf)
+    cb = torch.nn.functional.normalize(rnd(K, C), dim=-1)
+    cbb = cb.to(bf)
+    nc = L.vq_num_candidates(K)
+    cv, ci = torch.empty(R, nc, device=dev), torch.empty(R, nc, device=dev, dtype=torch.int32)
+    ind = torch.empty(R, device=dev, dtype=torch.int32)
+    t = timeit(lambda: L.call("ctc_vq_argmax", x, xb, R, C, cb, cbb, K, cv, ci, ind, L.stream_ptr()))
+    print(f"  vq_argmax (score GEMM N=8192 K=512 + refine; CTC_GEMM_ARGMAX_PAIR={os.environ.get('CTC_GEMM_ARGMAX_PAIR', '0')}): {t:8.1f} us")

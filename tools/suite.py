@@ -74,9 +74,20 @@ def main():
                 spatial_depth=4, temporal_depth=4, dim_head=32, heads=8)
     clip = CTCLIP(text_encoder=TextTower(), image_encoder=vit, dim_text=768, dim_image=294912, dim_latent=512)
     labels = torch.zeros(18)
-    dataset = [(volume(i), "no acute findings", labels, f"scan{i}", f"scan{i}.nii.gz") for i in range(args.volumes)]
-    loader = [(v.unsqueeze(0).pin_memory(), [t], labels.unsqueeze(0), [n], [p])
-              for i, (v, t, _, n, p) in enumerate(dataset) if i % world == rank]
+    # Only rank 0 ever indexes the dataset (the occlusion branch loads on rank 0 and broadcasts, visualizations.py:296-318);
+    # the other ranks hold just their own shard of volumes, so that 64 volumes x 221 MB are not replicated in every process.
+    sample = lambda i: (volume(i), "no acute findings", labels, f"scan{i}", f"scan{i}.nii.gz")
+    mine = {i: sample(i) for i in range(args.volumes) if rank == 0 or i % world == rank}
+
+    class Dataset:
+        def __len__(self):
+            return args.volumes
+
+        def __getitem__(self, i):
+            return mine[i]
+    dataset = Dataset()
+    loader = [(mine[i][0].unsqueeze(0).pin_memory(), [mine[i][1]], labels.unsqueeze(0), [mine[i][3]], [mine[i][4]])
+              for i in range(args.volumes) if i % world == rank]
     inf = CTClipInference(clip, batch_size=1, dataset=dataset, dataloader=loader, tokenizer=Tokenizer(),
                           results_folder=args.out)
     written = {"files": 0, "bytes": 0}
