@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU session H: ncu --set full with source of the epilogue-bound GEMM launches (FF1 + GEGLU + factors, dh + adjoint, out + residual)
+# GPU session H: ncu --set full with source of the epilogue-bound GEMM launches (FF1 + GEGLU + factors, dh + adjoint, out + residual, FF2 + residual)
 cd "${GRAFT_REPO_ROOT:-.}"
 O=gpurun_out
 timeout 200 python tools/prof_gemm.py all > $O/r2h_plain.log 2>&1 || { tail -20 $O/r2h_plain.log; exit 1; }

@@ -10,7 +10,7 @@ from ctclip_b200 import _lib as L
 
 dev = torch.device("cuda")
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
-impl = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+impl = (int(sys.argv[2]) if len(sys.argv) > 2 else 0) | L.GEMM_BPERM   # product path: direct epilogues (timing only: B is not permuted here)
 R = 8 * 24 * 24 * 24
 bf = torch.bfloat16
 
