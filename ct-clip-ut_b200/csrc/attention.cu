@@ -465,10 +465,13 @@ static int run_fwd(AttnParams& p, cudaStream_t st) {
     }
     return launch_attn<attn_fwd_kernel<QB, KBLK, HPC, PROBS, false>>(p, grid, HPC * (QB / 16) * 32, smem, st);
 }
-// The tcgen05 dQ kernel measures 621 us against 597 us for the mma.sync kernel at batch 8 (both bound by per-score
-// TMEM / shared-memory traffic at d_head = 32, profiles/r01_launches_step_b8_v2.md), so it is opt-in
-// (ctc_attention_set_tc_bwd) and the mma.sync kernel stays the default.
-static int g_tc_bwd = 0;
+// Spatial attention backward: mode 2 (default) = ONE pass on tcgen05 / TMEM (attention_tc_bwd.cu: 1 010 us per layer at
+// batch 8 against 1 245 us for the two mma.sync kernels in the same process, profiles/r02_kernel_bench_v5.log - once its
+// MMA-issue warp ran converged with uniform-register descriptors and its softmax warps in two groups on alternating
+// tiles); mode 0 = the two mma.sync kernels (dQ, dK/dV: the path for every other geometry and the cross-check of the
+// tests); mode 1 = tcgen05 dQ + mma.sync dK/dV (621 us against 597 us for dQ: never the default).
+// ctc_attention_set_tc_bwd / CTC_ATTN_BWD in the environment of the Python binding select a mode.
+static int g_tc_bwd = 2;
 static bool tc_bwd_eligible(const AttnParams& p) {
     return g_tc_bwd == 1 && p.bias_table != nullptr && p.mode == CTC_MODE_SPATIAL && p.n % 64 == 0 && p.W % 8 == 0 && p.n >= 64 &&
            (size_t)p.n * 192 + 60 * 1024 <= 220 * 1024;

@@ -108,7 +108,9 @@ attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
     const int n_mt = (n + TC_M - 1) / TC_M, n_kt = n_pad / TC_NT;
     const int n_tiles = n_mt * n_kt;
     if (warp == TC_WARP_MMA) {
-        if (lane == 0) {
+        // the whole warp walks the tile stream, one elected lane issues (elect_one: descriptors stay in uniform registers)
+        const bool issuer = elect_one();
+        {
             const uint32_t idesc_s = make_idesc_bf16(TC_M, TC_NT), idesc_o = make_idesc_bf16(TC_M, DH);
             auto issue_s = [&](int t) {                               // S(t) = Q(mt) K(kt)^T into S buffer t & 1
                 const int mt = t / n_kt, kt = t - mt * n_kt;
@@ -119,10 +121,10 @@ attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
                 const uint64_t dq = make_umma_desc_sw64(smem_u32(qs + (mt & 1) * TC_M * 64));
                 const uint64_t dk = make_umma_desc_sw64(smem_u32(ks + kt * TC_NT * 64));
                 const uint32_t ts = tmem_base + TC_COL_S + (t & 1) * TC_NT;
-                umma_f16_ss(ts, dq, dk, idesc_s, 0u);
-                umma_f16_ss(ts, dq + 2, dk + 2, idesc_s, 1u);         // second K16 step: +32 B inside the 64 B row
-                umma_commit(&s_full[t & 1]);
-                if (kt == n_kt - 1) umma_commit(&q_free[mt & 1]);     // every S of this M-tile has been issued
+                if (issuer) umma_f16_ss(ts, dq, dk, idesc_s, 0u);
+                if (issuer) umma_f16_ss(ts, dq + 2, dk + 2, idesc_s, 1u);         // second K16 step: +32 B inside the 64 B row
+                if (issuer) umma_commit(&s_full[t & 1]);
+                if (kt == n_kt - 1) if (issuer) umma_commit(&q_free[mt & 1]);     // every S of this M-tile has been issued
             };
             issue_s(0);
             if (n_tiles > 1) issue_s(1);
@@ -137,8 +139,8 @@ attn_tc_fwd_kernel(const AttnParams p, const float shift2) {
                 const uint32_t to = tmem_base + TC_COL_O + (mt & 1) * DH;
 #pragma unroll
                 for (int kk = 0; kk < TC_NT / 16; ++kk)
-                    umma_f16_ts(to, tp + kk * 8, dv + (uint64_t)(kk * 2), idesc_o, (kt > 0 || kk > 0) ? 1u : 0u);
-                umma_commit(&pv_done[b]);
+                    if (issuer) umma_f16_ts(to, tp + kk * 8, dv + (uint64_t)(kk * 2), idesc_o, (kt > 0 || kk > 0) ? 1u : 0u);
+                if (issuer) umma_commit(&pv_done[b]);
                 if (t + 2 < n_tiles) issue_s(t + 2);
             }
         }
@@ -353,7 +355,9 @@ attn_tc_bwd_dq_kernel(const AttnParams p) {
     const int n_mt = (n + TC_M - 1) / TC_M, n_kt = n_pad / TC_NT;
     const int n_tiles = n_mt * n_kt;
     if (warp == TQ_WARP_MMA) {
-        if (lane == 0) {
+        // the whole warp walks the tile stream, one elected lane issues (elect_one: descriptors stay in uniform registers)
+        const bool issuer = elect_one();
+        {
             const uint32_t idesc_s = make_idesc_bf16(TC_M, TC_NT), idesc_o = make_idesc_bf16(TC_M, DH);
             auto issue_s = [&](int t) {
                 const int mt = t / n_kt, kt = t - mt * n_kt;
@@ -366,12 +370,12 @@ attn_tc_bwd_dq_kernel(const AttnParams p) {
                 const uint64_t dk = make_umma_desc_sw64(smem_u32(ks + kt * TC_NT * 64));
                 const uint64_t dv = make_umma_desc_sw64(smem_u32(vs + kt * TC_NT * 64));
                 const uint32_t ts = tmem_base + TQ_COL_S + (t & 1) * TC_NT, tdp = tmem_base + TQ_COL_DP + (t & 1) * TC_NT;
-                umma_f16_ss(ts, dq_, dk, idesc_s, 0u);
-                umma_f16_ss(ts, dq_ + 2, dk + 2, idesc_s, 1u);
-                umma_f16_ss(tdp, dd, dv, idesc_s, 0u);
-                umma_f16_ss(tdp, dd + 2, dv + 2, idesc_s, 1u);
-                umma_commit(&s_full[t & 1]);
-                if (kt == n_kt - 1) umma_commit(&q_free[mt & 1]);
+                if (issuer) umma_f16_ss(ts, dq_, dk, idesc_s, 0u);
+                if (issuer) umma_f16_ss(ts, dq_ + 2, dk + 2, idesc_s, 1u);
+                if (issuer) umma_f16_ss(tdp, dd, dv, idesc_s, 0u);
+                if (issuer) umma_f16_ss(tdp, dd + 2, dv + 2, idesc_s, 1u);
+                if (issuer) umma_commit(&s_full[t & 1]);
+                if (kt == n_kt - 1) if (issuer) umma_commit(&q_free[mt & 1]);
             };
             issue_s(0);
             if (n_tiles > 1) issue_s(1);
@@ -386,8 +390,8 @@ attn_tc_bwd_dq_kernel(const AttnParams p) {
                 const uint32_t tdq = tmem_base + TQ_COL_DQ + (mt & 1) * DH;
 #pragma unroll
                 for (int kk = 0; kk < TC_NT / 16; ++kk)
-                    umma_f16_ts(tdq, tds + kk * 8, db + (uint64_t)(kk * 2), idesc_o, (kt > 0 || kk > 0) ? 1u : 0u);
-                umma_commit(&pv_done[b]);
+                    if (issuer) umma_f16_ts(tdq, tds + kk * 8, db + (uint64_t)(kk * 2), idesc_o, (kt > 0 || kk > 0) ? 1u : 0u);
+                if (issuer) umma_commit(&pv_done[b]);
                 if (t + 2 < n_tiles) issue_s(t + 2);
             }
         }

@@ -33,6 +33,7 @@ static constexpr int OB_SOFTMAX_WARPS = 16;                        // four per T
 static constexpr int OB_WARP_DRAIN_V = 16, OB_WARP_DRAIN_K = 17;    // warp % 4 = 0 / 1: TMEM lanes 0-31 (dV^T) / 32-63 (dK^T)
 static constexpr int OB_WARP_MMA = 18, OB_WARP_LOAD = 19;
 static constexpr int OB_THREADS = 20 * 32;
+static constexpr int OB_STG = 2 * 8192;                              // bytes of one P / dS staging buffer (128 queries)
 static constexpr int OB_MAX_MT = 5;                                // n <= 640
 static constexpr uint32_t OB_TMEM_COLS = 512;
 static constexpr uint32_t OB_COL_S = 0, OB_COL_DP = 64, OB_COL_DS = 128, OB_COL_DQ = 160, OB_COL_DVK = 320;   // dVK: 2 x 64
@@ -52,9 +53,9 @@ CTC_DEVINL ObSmem __host__ ob_layout(int n_rows, int nb) {
     L.qs = o;   o += n_rows * 64;                                  // [n_rows][64 B]  q^ * scale * log2e   SWIZZLE_64B
     L.dos = o;  o += n_rows * 64;                                  // [n_rows][64 B]  dO                   SWIZZLE_64B
     L.tT = o;   o += (n_rows / 64) * 8192;                         // [n_rows/64][64 rows: dO^T | (q^)^T][128 B]  SWIZZLE_128B
-    L.stg = o;  o += 2 * 8192;                                     // [2][64 rows: P keys | dS keys][128 B = 64 queries]
+    L.stg = o;  o += 2 * OB_STG;                                   // [2 buffers][2 blocks of 64 queries][64 rows: P keys | dS keys][128 B]
     L.kt = o;   o += 2 * 6144;                                     // [2] x { K^ 32 x 64 B | V | (K^)^T }  SWIZZLE_64B
-    L.pair = o; o += ((nb + 1) & ~1) * 8;
+    L.pair = o; o += ((nb + 1 + 3) & ~3) * 4;                      // fp32 bias table * log2e, one leading zero (index -1)
     L.tab8 = o; o += ((n_rows / 8 + 3) & ~3) * 4;
     L.lse2 = o; o += n_rows * 4;
     L.dl = o;   o += n_rows * 4;
@@ -76,11 +77,16 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
     const int n_mt = (n + TC_M - 1) / TC_M, n_rows = n_mt * TC_M, n_kt = n / OB_NK;
     const int nW = 2 * p.W - 1, nb = (2 * p.H - 1) * nW;
     const ObSmem L = ob_layout(n_rows, nb);
+    {
+        uint32_t dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if ((uint32_t)(smb - sm_raw) + (uint32_t)L.total > dyn) __trap();
+    }
     uint8_t* qs = smb + L.qs;   uint8_t* dos = smb + L.dos;
     uint8_t* tT = smb + L.tT;
     uint8_t* stg = smb + L.stg;
     uint8_t* ktl = smb + L.kt;
-    float2* pair = reinterpret_cast<float2*>(smb + L.pair);
+    float* tabf = reinterpret_cast<float*>(smb + L.pair) + 1;      // tabf[-1] = 0
     int* tab8 = reinterpret_cast<int*>(smb + L.tab8);
     float* lse2 = reinterpret_cast<float*>(smb + L.lse2);
     float* dl = reinterpret_cast<float*>(smb + L.dl);
@@ -88,27 +94,28 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
     float* tr = reinterpret_cast<float*>(smb + L.tr);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smb + L.bars);
     uint64_t *s_full = bars, *s_free = bars + 2, *p_full = bars + 4, *ds_free = bars + 6, *k_full = bars + 8,
-             *k_free = bars + 10, *kv_full = bars + 12, *kv_free = bars + 14, *stg_free = bars + 16, *dq_done = bars + 17;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+             *k_free = bars + 10, *kv_full = bars + 12, *kv_free = bars + 14, *stg_free = bars + 16, *dq_done = bars + 18;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
     const long long ldo = (long long)p.heads * DH;
 
     if (threadIdx.x < 32) sv[threadIdx.x] = p.q_scale[threadIdx.x];
     else if (threadIdx.x < 64) sv[threadIdx.x] = p.k_scale[threadIdx.x - 32];
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&s_full[b], 1);  mbar_init(&s_free[b], OB_SOFTMAX_WARPS);
-            mbar_init(&p_full[b], OB_SOFTMAX_WARPS);  mbar_init(&ds_free[b], 1);
+            mbar_init(&s_full[b], 1);  mbar_init(&s_free[b], OB_SOFTMAX_WARPS / 2);
+            mbar_init(&p_full[b], OB_SOFTMAX_WARPS / 2);  mbar_init(&ds_free[b], 1);
             mbar_init(&k_full[b], 1);  mbar_init(&k_free[b], 1);
             mbar_init(&kv_full[b], 1); mbar_init(&kv_free[b], 2);
+            mbar_init(&stg_free[b], 1);
         }
-        mbar_init(stg_free, 1);
         mbar_init(dq_done, 1);
         fence_barrier_init();
     }
     {
         const float* tb = p.bias_table + (long long)head * nb;
         for (int k = threadIdx.x; k < nb; k += blockDim.x)
-            pair[k] = make_float2(tb[k] * LOG2E, k > 0 ? tb[k - 1] * LOG2E : 0.f);
+            tabf[k] = tb[k] * LOG2E;
+        if (threadIdx.x == 0) tabf[-1] = 0.f;
         for (int jb = threadIdx.x; jb < n_rows / 8; jb += blockDim.x) {
             const int j = min(jb * 8, n - 8);
             tab8[jb] = (j / p.W) * nW + (j % p.W);
@@ -176,7 +183,9 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
     const int n_tiles = n_kt * n_mt;
 
     if (warp == OB_WARP_MMA) {
-        if (lane == 0) {
+        // the whole warp walks the tile stream, one elected lane issues (elect_one: descriptors stay in uniform registers)
+        const bool issuer = elect_one();
+        {
             const uint32_t idesc = make_idesc_bf16(TC_M, OB_NK), idesc_vk = make_idesc_bf16(TC_M, 2 * OB_NK);
             auto issue_s = [&](int t, int kt, int mt) {               // S(t), dP(t) into buffer t & 1
                 const int b = t & 1;
@@ -188,11 +197,11 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
                 const uint64_t dk = make_umma_desc_sw64(smem_u32(kb));
                 const uint64_t dv = make_umma_desc_sw64(smem_u32(kb + 2048));
                 const uint32_t ts = tmem_base + OB_COL_S + b * OB_NK, tdp = tmem_base + OB_COL_DP + b * OB_NK;
-                umma_f16_ss(ts, dq_, dk, idesc, 0u);
-                umma_f16_ss(ts, dq_ + 2, dk + 2, idesc, 1u);          // second K16 step: +32 B inside the 64 B row
-                umma_f16_ss(tdp, dd, dv, idesc, 0u);
-                umma_f16_ss(tdp, dd + 2, dv + 2, idesc, 1u);
-                umma_commit(&s_full[b]);
+                if (issuer) umma_f16_ss(ts, dq_, dk, idesc, 0u);
+                if (issuer) umma_f16_ss(ts, dq_ + 2, dk + 2, idesc, 1u);          // second K16 step: +32 B inside the 64 B row
+                if (issuer) umma_f16_ss(tdp, dd, dv, idesc, 0u);
+                if (issuer) umma_f16_ss(tdp, dd + 2, dv + 2, idesc, 1u);
+                if (issuer) umma_commit(&s_full[b]);
             };
             // (kt, mt) of tile t + 2, advanced alongside the loop (no integer divisions in the tile stream)
             int kt2 = 0, mt2 = 0;
@@ -219,23 +228,23 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
                     const uint32_t tdq = tmem_base + OB_COL_DQ + mt * DH;
 #pragma unroll
                     for (int kk = 0; kk < OB_NK / 16; ++kk)
-                        umma_f16_ts(tdq, tds + kk * 8, dkT + (uint64_t)(kk * 2), idesc, (kt > 0 || kk > 0) ? 1u : 0u);
-                    umma_commit(&ds_free[b]);
+                        if (issuer) umma_f16_ts(tdq, tds + kk * 8, dkT + (uint64_t)(kk * 2), idesc, (kt > 0 || kk > 0) ? 1u : 0u);
+                    if (issuer) umma_commit(&ds_free[b]);
                     // [dV^T ; dK^T][kt] += [dO^T ; Q^^T](mt) [P ; dS](t)^T    (reduction over the 128 queries of the M-tile)
                     const uint64_t a0 = make_umma_desc_sw128(smem_u32(tT) + (uint32_t)(mt * 2) * 8192u);
-                    const uint64_t b0 = make_umma_desc_sw128(smem_u32(stg));
+                    const uint64_t b0 = make_umma_desc_sw128(smem_u32(stg) + (uint32_t)(b * OB_STG));
 #pragma unroll
                     for (int kk = 0; kk < TC_M / 16; ++kk) {
                         // +512 in the (addr >> 4) field = the next 8 KB block; +2 = the next 16 queries (32 B) of a row
                         const uint64_t off = (uint64_t)((kk >> 2) * 512 + (kk & 3) * 2);
-                        umma_f16_ss(tvk, a0 + off, b0 + off, idesc_vk, (mt > 0 || kk > 0) ? 1u : 0u);
+                        if (issuer) umma_f16_ss(tvk, a0 + off, b0 + off, idesc_vk, (mt > 0 || kk > 0) ? 1u : 0u);
                     }
-                    umma_commit(stg_free);
-                    if (mt == n_mt - 1) { umma_commit(&kv_full[kt & 1]); umma_commit(&k_free[kt & 1]); }
+                    if (issuer) umma_commit(&stg_free[b]);
+                    if (mt == n_mt - 1) { if (issuer) umma_commit(&kv_full[kt & 1]); if (issuer) umma_commit(&k_free[kt & 1]); }
                     if (!ahead && t + 2 < n_tiles) { issue_s(t + 2, kt2, mt2); advance2(); }
                 }
             }
-            umma_commit(dq_done);
+            if (issuer) umma_commit(dq_done);
         }
     } else if (warp == OB_WARP_LOAD) {
         // K^ (normalised), V and (K^)^T of key tile kt; lane = key
@@ -347,70 +356,80 @@ attn_tc_bwd_onepass_kernel(const AttnParams p) {
             __syncwarp();
         }
     } else {
-        const int quarter = warp & 3, cpart = warp >> 2;              // TMEM lane quarter; 8-key slice of the 32-key tile
+        // Two groups of 8 softmax warps work on ALTERNATING tiles (group = tile parity = S / dP / dS / staging buffer), so
+        // that the latency chain of one tile (barrier wake-up, TMEM loads, exponentials, TMEM store, staging stores, proxy
+        // fence) overlaps the next tile's instead of all 16 warps walking it tile after tile (ncu: both pipes ~35 % busy).
+        const int quarter = warp & 3, grp = warp >> 3, half = (warp >> 2) & 1;   // TMEM lane quarter; tile parity; 16-key half
         const int r = quarter * 32 + lane;                            // query row of the M-tile = TMEM lane
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        // per-thread constants of the tile stream, computed once: the bias-table base of this thread's row in every
-        // M-tile, and the staging addresses of its 8 keys (P row c, dS row 32 + c of the 64-query block r / 64)
+        const int b = grp;
+        // per-thread constants of the tile stream: the bias-table base of this thread's row in every M-tile and the staging
+        // addresses of its keys (P row c, dS row 32 + c of the 64-query block r / 64); key k + 8 sits 8 rows further
         int base_m[OB_MAX_MT];
 #pragma unroll
         for (int m = 0; m < OB_MAX_MT; ++m) base_m[m] = bias_base(p, m * TC_M + r);
         uint32_t soff[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            soff[k] = smem_u32(stg) + (uint32_t)((r >> 6) * 8192 + (cpart * 8 + k) * 128 + ((((r & 63) >> 3) ^ k) << 4) + (r & 7) * 2);
-        const uint32_t ts0 = tmem_base + OB_COL_S + lane_sel + cpart * 8, tdp0 = tmem_base + OB_COL_DP + lane_sel + cpart * 8;
-        const uint32_t tds0 = tmem_base + OB_COL_DS + lane_sel + cpart * 4;
-        int t = 0;
-        for (int kt = 0; kt < n_kt; ++kt) {
-            const int tb0 = tab8[kt * (OB_NK / 8) + cpart];
+            soff[k] = smem_u32(stg) + (uint32_t)(b * OB_STG + (r >> 6) * 8192 + (half * 16 + k) * 128 + ((((r & 63) >> 3) ^ k) << 4) + (r & 7) * 2);
+        const uint32_t ts0 = tmem_base + OB_COL_S + lane_sel + b * OB_NK + half * 16;
+        const uint32_t tdp0 = tmem_base + OB_COL_DP + lane_sel + b * OB_NK + half * 16;
+        const uint32_t tds0 = tmem_base + OB_COL_DS + lane_sel + b * (OB_NK / 2) + half * 8;
+        int kt = 0, mt = grp;
+        if (mt >= n_mt) { mt -= n_mt; ++kt; }                          // n_mt == 1
 #pragma unroll 1
-            for (int mt = 0; mt < n_mt; ++mt, ++t) {
-                const int b = t & 1;
-                const int i = mt * TC_M + r;
-                // select chain instead of base_m[mt]: a dynamically indexed array would live in local memory
-                const int base_i = mt == 0 ? base_m[0] : mt == 1 ? base_m[1] : mt == 2 ? base_m[2] : mt == 3 ? base_m[3] : base_m[4];
-                const float2* prow = pair + (base_i - tb0);
-                const float lse2_i = lse2[i], d_i = dl[i];
-                mbar_wait(&s_full[b], (t >> 1) & 1);
-                tcgen05_fence_after();
-                uint32_t vs_[8], vd_[8];
-                tmem_ld_32x32b_x8(ts0 + b * OB_NK, vs_);
-                tmem_ld_32x32b_x8(tdp0 + b * OB_NK, vd_);
-                tmem_ld_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_free[b]);               // S / dP buffer b may be overwritten (tile t + 2)
-                uint32_t pkP[4], pkD[4];
+        for (int t = grp; t < n_tiles; t += 2) {
+            const int it = t >> 1;                                    // this group's tile counter = use count of buffer b
+            const int tb0 = tab8[kt * (OB_NK / 8) + half * 2], tb1 = tab8[kt * (OB_NK / 8) + half * 2 + 1];
+            const int i = mt * TC_M + r;
+            // select chain instead of base_m[mt]: a dynamically indexed array would live in local memory
+            const int base_i = mt == 0 ? base_m[0] : mt == 1 ? base_m[1] : mt == 2 ? base_m[2] : mt == 3 ? base_m[3] : base_m[4];
+            const float lse2_i = lse2[i], d_i = dl[i];
+            mbar_wait(&s_full[b], it & 1);
+            tcgen05_fence_after();
+            uint32_t vs_[16], vd_[16];
+            tmem_ld_32x32b_x16(ts0, vs_);
+            tmem_ld_32x32b_x16(tdp0, vd_);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[b]);                   // S / dP buffer b may be overwritten (tile t + 2)
+            uint32_t pkP[8], pkD[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float2 f = prow[-2 * u];
-                    const float p0 = fast_exp2(__uint_as_float(vs_[2 * u]) + f.x - lse2_i);
-                    const float p1 = fast_exp2(__uint_as_float(vs_[2 * u + 1]) + f.y - lse2_i);
-                    pkP[u] = pack_bf16(p0, p1);
-                    pkD[u] = pack_bf16(p0 * (__uint_as_float(vd_[2 * u]) - d_i), p1 * (__uint_as_float(vd_[2 * u + 1]) - d_i));
-                }
-                if (t >= 2) {                                         // dS(t-2) consumed by its dQ MMAs
-                    mbar_wait(&ds_free[b], ((t >> 1) - 1) & 1);
-                    tcgen05_fence_after();
-                }
-                tmem_st_32x32b_x4(tds0 + b * (OB_NK / 2), pkD);
-                if (t >= 1) mbar_wait(stg_free, (t - 1) & 1);         // staging consumed by the dV / dK MMAs of tile t-1
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // st.shared.u16 stores the low half of the register: the odd key needs one shift
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(soff[2 * u]), "h"((uint16_t)(pkP[u] & 0xFFFFu)) : "memory");
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(soff[2 * u + 1]), "h"((uint16_t)(pkP[u] >> 16)) : "memory");
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(soff[2 * u] + 4096u), "h"((uint16_t)(pkD[u] & 0xFFFFu)) : "memory");
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(soff[2 * u + 1] + 4096u), "h"((uint16_t)(pkD[u] >> 16)) : "memory");
-                }
-                tmem_st_wait();
-                fence_proxy_async();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[b]);
+            for (int u = 0; u < 8; ++u) {
+                const float* prow = tabf + (base_i - (u < 4 ? tb0 : tb1));
+                const int uu = u & 3;
+                const float p0 = fast_exp2(__uint_as_float(vs_[2 * u]) + prow[-2 * uu] - lse2_i);
+                const float p1 = fast_exp2(__uint_as_float(vs_[2 * u + 1]) + prow[-2 * uu - 1] - lse2_i);
+                pkP[u] = pack_bf16(p0, p1);
+                pkD[u] = pack_bf16(p0 * (__uint_as_float(vd_[2 * u]) - d_i), p1 * (__uint_as_float(vd_[2 * u + 1]) - d_i));
             }
+            if (it >= 1) {                                            // dS(t-2) consumed by its dQ MMAs
+                mbar_wait(&ds_free[b], (it - 1) & 1);
+                tcgen05_fence_after();
+            }
+            tmem_st_32x32b_x4(tds0, reinterpret_cast<const uint32_t(&)[4]>(pkD[0]));
+            tmem_st_32x32b_x4(tds0 + 4, reinterpret_cast<const uint32_t(&)[4]>(pkD[4]));
+            // staging buffer b consumed by the dV / dK MMAs of tile t - 2 (the MMAs of tile t - 1 read the other buffer)
+            if (it >= 1) mbar_wait(&stg_free[b], (it - 1) & 1);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                // keys 2u, 2u + 1 of this warp's 16: staging rows (half * 16 + key); st.shared.u16 stores the low register half
+                const uint32_t a0 = soff[(2 * u) & 7] + (uint32_t)((2 * u) >> 3) * 1024u, a1 = soff[(2 * u + 1) & 7] + (uint32_t)((2 * u + 1) >> 3) * 1024u;
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(a0), "h"((uint16_t)(pkP[u] & 0xFFFFu)) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(a1), "h"((uint16_t)(pkP[u] >> 16)) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(a0 + 4096u), "h"((uint16_t)(pkD[u] & 0xFFFFu)) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(a1 + 4096u), "h"((uint16_t)(pkD[u] >> 16)) : "memory");
+            }
+            tmem_st_wait();
+            fence_proxy_async();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[b]);
+            mt += 2;
+            if (mt >= n_mt) { mt -= n_mt; ++kt; if (mt >= n_mt) { mt -= n_mt; ++kt; } }
         }
+        const int cpart = warp >> 2;
         if (cpart == 0) {                                             // one warp per lane quarter finishes the dQ rows
             mbar_wait(dq_done, 0);
             tcgen05_fence_after();
@@ -476,8 +495,10 @@ bool tc_bwd_onepass_eligible(const AttnParams& p) {
 int run_tc_bwd_onepass(const AttnParams& p, cudaStream_t st) {
     const int n_rows = ((p.n + TC_M - 1) / TC_M) * TC_M;
     const ObSmem L = ob_layout(n_rows, (2 * p.H - 1) * (2 * p.W - 1));
-    const size_t smem = (size_t)L.total + 1024;
-    CTC_REQUIRE(smem <= 227 * 1024, "attention one-pass backward: %zu bytes of shared memory exceed 227 KB", smem);
+    // up to 1023 bytes of slack for the 1024-byte alignment of the swizzled tiles; at n = 576 the layout leaves only 312
+    // (dynamic shared memory starts 1024-aligned in practice; the kernel traps if the aligned layout does not fit)
+    CTC_REQUIRE((size_t)L.total <= 227 * 1024, "attention one-pass backward: %d bytes of shared memory exceed 227 KB", L.total);
+    const size_t smem = (size_t)L.total + 1024 <= 227 * 1024 ? (size_t)L.total + 1024 : (size_t)227 * 1024;
     static size_t configured_dev[kMaxDevices] = {};
     size_t& configured = configured_dev[current_device()];
     if (smem > configured) {

@@ -226,6 +226,16 @@ CTC_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thr
 CTC_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16/fp16 in, fp32 accumulate), single CTA
+// One lane of a CONVERGED warp (elect.sync).  The tcgen05 issue loops run with the whole warp walking the pipeline and
+// only the instructions themselves under `if (elect)`: inside an `if (lane == 0)` region the compiler cannot prove that
+// descriptors / addresses are warp-uniform and wraps EVERY tcgen05.mma / commit in a scalarisation loop (ELECT,
+// 5 x R2UR.BROADCAST, BRA.U.ANY: ~18 SASS instructions per MMA on one thread), which paced the K <= 512 GEMMs and the
+// attention kernels; computed in converged code the operands live in uniform registers.
+CTC_DEVINL bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 CTC_DEVINL void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

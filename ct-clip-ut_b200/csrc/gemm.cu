@@ -512,7 +512,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        // whole warp converged, one elected lane issues (see elect_one): addresses / coordinates stay in uniform registers
+        {
+            const bool issuer = elect_one();
             int stage = 0; uint32_t phase = 0;
             for (int tile = unit; tile < num_tiles; tile += n_units) {
                 const int tm = tile / tiles_n, tn = tile % tiles_n;
@@ -523,21 +525,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if constexpr (CG == 2) {
                         // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
                         const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-                        tma_load_2d_cg2(sa, &tmap_a, fb, kb * BK, tm * TM + (int)rank * BM);
-                        tma_load_2d_cg2(sb, &tmap_b, fb, kb * BK, tn * BN + (int)rank * (BN / 2));
+                        if (issuer) {
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+                            tma_load_2d_cg2(sa, &tmap_a, fb, kb * BK, tm * TM + (int)rank * BM);
+                            tma_load_2d_cg2(sb, &tmap_b, fb, kb * BK, tn * BN + (int)rank * (BN / 2));
+                        }
                     } else {
-                        mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                        if (issuer) {
+                            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+                            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, tm * BM);
+                            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, tn * BN);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && rank == 0) {
+        // The whole warp walks the pipeline and one elected lane issues (see elect_one): every descriptor is computed in
+        // converged code, so the tcgen05 instructions take uniform registers without a scalarisation loop.
+        if (rank == 0) {
+            const bool issuer = elect_one();
             constexpr uint32_t idesc = make_idesc_bf16(TM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -552,22 +562,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t sb = sa + S::kABytes;
                     const uint64_t da = make_umma_desc_sw128(sa);
                     const uint64_t db = make_umma_desc_sw128(sb);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr>>4) field
-                        if constexpr (CG == 2)
-                            umma_f16_ss_cg2(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr>>4) field
+                            if constexpr (CG == 2)
+                                umma_f16_ss_cg2(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                                (kb > 0 || k > 0) ? 1u : 0u);
+                            else
+                                umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
                                             (kb > 0 || k > 0) ? 1u : 0u);
-                        else
-                            umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                        (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        // frees the smem slot (of both CTAs in pair mode) once these MMAs retire
+                        if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     }
-                    // frees the smem slot (of both CTAs in pair mode) once these MMAs retire
-                    if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 // accumulator complete -> epilogue (of both CTAs)
-                if constexpr (CG == 2) umma_commit_cg2(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+                if (issuer) {
+                    if constexpr (CG == 2) umma_commit_cg2(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

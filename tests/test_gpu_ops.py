@@ -241,6 +241,17 @@ def test_attention_bwd_dq_on_tcgen05(lib, B, T, H, W, heads):
 
 
 @pytest.mark.parametrize("B,T,H,W,heads", [(1, 2, 24, 24, 8), (1, 3, 8, 8, 2), (2, 1, 16, 8, 1), (1, 1, 16, 24, 3)])
+def test_attention_bwd_two_kernel_mma_sync_path(lib, B, T, H, W, heads):
+    """The two mma.sync kernels (dQ, dK/dV) - the default until the one-pass tcgen05 kernel overtook them, still the path of
+    every geometry that kernel does not take - forced with ctc_attention_set_tc_bwd(0)."""
+    prev = lib.load().ctc_attention_set_tc_bwd(0)
+    try:
+        _attention_fwd_bwd_probs(lib, 0, B, T, H, W, heads)
+    finally:
+        lib.load().ctc_attention_set_tc_bwd(prev)
+
+
+@pytest.mark.parametrize("B,T,H,W,heads", [(1, 2, 24, 24, 8), (1, 3, 8, 8, 2), (2, 1, 16, 8, 1), (1, 1, 16, 24, 3)])
 def test_attention_bwd_one_pass_on_tcgen05(lib, B, T, H, W, heads):
     """dQ, dK and dV from ONE recomputation of the probabilities on tcgen05 / TMEM (attention_tc_bwd.cu), against the
     same torch fp32 reference as the two-kernel mma.sync path; twice, and bit-identical (no atomics)."""

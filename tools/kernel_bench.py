@@ -78,7 +78,9 @@ for mode, tag in ((1, "attn_t"), (0, "attn_s")):
     def bwd():
         L.call("ctc_attention_bwd", q, inner, kv, kv.data_ptr() + inner * 2, 2 * inner, o, d_o, lse, B, T, H, W, heads,
                qs, ks, 8.0, table, mode, dq, inner, dkv, dkv.data_ptr() + inner * 2, 2 * inner, delta, L.stream_ptr())
+    prev_mode = L.load().ctc_attention_set_tc_bwd(0)
     print(f"  {tag} fwd {timeit(fwd):8.1f} us   bwd (dq + dkv, mma.sync) {timeit(bwd):8.1f} us")
+    L.load().ctc_attention_set_tc_bwd(prev_mode)
     if mode == 0:
         lib = L.load()
         lib.ctc_attention_set_tc_bwd(2)
@@ -86,6 +88,7 @@ for mode, tag in ((1, "attn_t"), (0, "attn_s")):
         ref = (dq.clone(), dkv.clone())
         lib.ctc_attention_set_tc_bwd(0)
         bwd(); torch.cuda.synchronize()
+        lib.ctc_attention_set_tc_bwd(prev_mode)
         err = max(float((dq.float() - ref[0].float()).abs().max() / dq.float().abs().max()),
                   float((dkv.float() - ref[1].float()).abs().max() / dkv.float().abs().max()))
         print(f"  {tag} bwd one pass on tcgen05 (dq, dk, dv) {t1:8.1f} us   (max rel diff to the mma.sync kernels {err:.2e})")
