@@ -640,14 +640,25 @@ def run_product(args):
     attribution = None
     del bufs, vol, grad, ctx, graph
     torch.cuda.empty_cache()
+    # The latency mode shards the windows / alpha steps of ONE volume over the ranks, so every rank must hold the SAME
+    # volume (the throughput batches above are seeded per rank): rank 0's first volume, regenerated from its seed on the
+    # other ranks (the first 55.3 M numbers of the same generator) - no collective before the timed region.
+    attr_host = host[:1]
+    if world > 1 and rank != 0 and not (args.no_attribution and args.no_parity):
+        g0 = torch.Generator().manual_seed(1234)
+        attr_host = (0.35 * torch.randn(1, 1, 240, 480, 480, generator=g0) - 0.2).clamp_(-1, 1)
+        attr_host[:, :, :16] = -1; attr_host[:, :, -16:] = -1
+        attr_host[:, :, :, :40] = -1; attr_host[:, :, :, -40:] = -1
+        attr_host[..., :40] = -1; attr_host[..., -40:] = -1
+        attr_host = attr_host.pin_memory()
     if not args.no_attribution:
-        attribution = run_attribution(eng, host[:1], tl, dev, world, dist)
+        attribution = run_attribution(eng, attr_host, tl, dev, world, dist)
 
     # ---- N > 1: the sharded path must reproduce the single-rank result (untimed; every rank takes part)
     parity = None
     if world > 1 and not args.no_parity:
         from ctclip_b200.selfcheck import sharding_parity
-        parity = sharding_parity(eng, host[:1].to(dev), tl)
+        parity = sharding_parity(eng, attr_host.to(dev), tl)
         torch.cuda.empty_cache()
 
     # ---- same-box comparators (rank 0, N = 1): cuBLAS on the step's GEMM shapes, the reference's PyTorch GPU path
