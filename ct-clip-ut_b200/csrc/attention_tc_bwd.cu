@@ -6,10 +6,11 @@
 // outer loop, the query M-tile the inner one, so that
 //   dQ   [M-tile][128 x 32]  accumulates over the outer loop in n_mt <= 5 resident TMEM accumulators (160 columns),
 //   dV^T, dK^T [32 x 32 keys] accumulate over the inner loop (double-buffered, drained once per key tile).
-// Per tile t (b = t & 1):
+// Per tile t (b = t & 1); the MMA warp runs converged and one elected lane issues (common.cuh: elect_one):
 //   MMA thread   : S = Q^ K^T, dP = dO V^T                (SS, M128 N32 K32)            -> TMEM S[b], dP[b]
-//   softmax warps: thread = query row i (lse_i, D_i from shared memory): p = exp2(s + bias - lse_i), dS = p (dP - D_i)
-//                  dS as bf16 -> TMEM dS[b] (A operand of the dQ MMA); P and dS as bf16 -> shared-memory staging tiles
+//   softmax warps: two groups of 8 warps on ALTERNATING tiles (group = b), thread = query row i, 16 keys per warp
+//                  (lse_i, D_i from shared memory): p = exp2(s + bias - lse_i), dS = p (dP - D_i)
+//                  dS as bf16 -> TMEM dS[b] (A operand of the dQ MMA); P and dS as bf16 -> shared-memory staging tiles [b]
 //                  in [key][query] order (K-major B operands of the dV / dK MMAs)
 //   MMA thread   : dQ[mt]  += dS K^                        (TS, A = dS from TMEM, B = K^ transposed tile)
 //                  [dV^T ; dK^T][kt] += [dO^T ; Q^^T] [P ; dS]^T   ONE SS stream, M128 N64 K128: the A operand stacks the

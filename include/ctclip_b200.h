@@ -132,10 +132,11 @@ int ctc_attention_fwd_tc(const void* q, int64_t ldq, const void* k, const void* 
 /* Spatial forward kernel: compute every other exponential of the softmax with an FMA-pipe polynomial instead of
  * MUFU.EX2 (the FA4 split).  Off by default - it measured 21 % slower here; returns the previous setting. */
 int ctc_attention_set_exp2_poly(int on);
-/* Spatial backward on tcgen05 / TMEM, opt-in: mode 1 = dQ only (measured 4 % slower than the mma.sync kernel),
- * mode 2 = dQ, dK and dV in ONE pass (attention_tc_bwd.cu; same result to bf16 rounding, bit-reproducible; measured
- * 1750 us against 1372 us for the two mma.sync kernels at batch 8), 0 = mma.sync (default).  Returns the previous
- * setting (NOT a status code). */
+/* Which kernels ctc_attention_bwd runs for spatial sequences: mode 2 (default) = dQ, dK and dV in ONE pass on
+ * tcgen05 / TMEM (attention_tc_bwd.cu; 1 010 us against 1 245 us for the two mma.sync kernels at batch 8; same result to
+ * bf16 rounding, bit-reproducible) where the geometry allows (bias table, n % 32 == 0, 64 <= n <= 640, W % 8 == 0),
+ * mode 0 = the two mma.sync kernels (every other geometry always takes them), mode 1 = tcgen05 dQ + mma.sync dK/dV
+ * (4 % slower than mode 0).  Returns the previous setting (NOT a status code). */
 int ctc_attention_set_tc_bwd(int mode);
 int ctc_attention_score_bound(const float* q_scale, const float* k_scale, float scale, const float* bias_table,
                               int heads, int H, int W, float* bound_dev, void* stream);
