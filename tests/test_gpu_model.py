@@ -142,3 +142,32 @@ def test_full_backward_vs_oracle(no_tf32):
     assert rms < 8e-3
     assert pr > 0.999
     assert pt > 0.999
+
+
+@pytest.mark.parametrize("size", ["tiny", "full"])
+def test_permuted_weights_and_direct_epilogues_change_no_bit(no_tf32, size):
+    """Plan(direct_epilogue=True) permutes the rows of every GEMM weight inside groups of 32 and selects the staging-free
+    epilogues; Plan(direct_epilogue=False) keeps the nn.Linear layout and the staged epilogues.  Same
+    accumulators, same rounding: every activation, the VQ codes, the logit and the input gradient must be bit-identical."""
+    from ctclip_b200.engine import Engine
+    from ctclip_b200.plan import Config, Plan
+    cfg_o = O.TINY if size == "tiny" else O.FULL
+    cfg = Config(dim=cfg_o.dim, codebook_size=cfg_o.codebook_size, image_size=cfg_o.image_size,
+                 patch_size=cfg_o.patch_size, temporal_patch_size=cfg_o.temporal_patch_size,
+                 spatial_depth=cfg_o.spatial_depth, temporal_depth=cfg_o.temporal_depth, dim_head=cfg_o.dim_head,
+                 heads=cfg_o.heads, dim_text=cfg_o.dim_text, dim_latent=cfg_o.dim_latent)
+    sd = O.init_state_dict(cfg_o, 42)
+    vol = O.synthetic_volume(cfg_o, 0, batch=2 if size == "tiny" else 1).to(DEV)
+    txt = O.synthetic_text_embeds(cfg_o, 7, batch=vol.shape[0]).to(DEV)
+    outs = []
+    for direct in (True, False):
+        plan = Plan(sd, cfg, DEV, direct_epilogue=direct)
+        assert bool(plan.gemm_flags) == direct
+        eng = Engine(plan)
+        ctx = eng.forward(vol, eng.text_latents(txt), save=True)
+        grad = eng.backward(ctx)
+        torch.cuda.synchronize()
+        outs.append((ctx.x_pre_vq.clone(), ctx.indices.clone(), ctx.sim.clone(), grad.clone()))
+        del eng, plan, ctx
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
