@@ -454,7 +454,14 @@ def run_product(args):
     host[:, :, :16] = -1; host[:, :, -16:] = -1
     host[:, :, :, :40] = -1; host[:, :, :, -40:] = -1
     host[..., :40] = -1; host[..., -40:] = -1
-    host = host.pin_memory()
+    # the scans as a NIfTI file stores them: int16 Hounsfield units (slope 1, intercept 0, already at the target spacing
+    # and shape, so that `process_file`'s arithmetic reduces to clamp(hu) / 1000); every arm of the bench runs on exactly
+    # these volumes - the fp32 tensors ARE preprocess(hu)
+    hu = (host * 1000).round_().to(torch.int16).squeeze(1)                                       # [B, D, H, W]
+    host = (hu.float() / 1000).unsqueeze(1).contiguous().pin_memory()
+    # NIfTI file order: the first axis (i = H) fastest, then j = W, then k = D - the bytes a reader hands over unchanged
+    host_raw = hu.permute(0, 1, 3, 2).contiguous().pin_memory()                                  # memory [B, D, W, H]
+    del hu
     text = torch.randn(1, 768, generator=torch.Generator().manual_seed(7)).to(dev)
     vol = host.to(dev)
     tl = eng.text_latents(text)
@@ -517,14 +524,26 @@ def run_product(args):
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    # int16 ingest (what `CTClipInference` / `DeviceLoader` do with a .nii.gz scan): the step's inputs are the RAW int16
+    # voxels, `process_volume` (the reference's process_file arithmetic, one fused kernel per scan) runs on the device
+    from ctclip_b200.preprocess import process_volume
+    raw_bufs = [torch.empty(host_raw.shape, dtype=torch.int16, device=dev) for _ in range(2)]
+    ingest = {"raw": False}
+
     def issue_h2d(i):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[i % 2])
-            bufs[i % 2].copy_(host, non_blocking=True)
+            if ingest["raw"]:
+                raw_bufs[i % 2].copy_(host_raw, non_blocking=True)
+            else:
+                bufs[i % 2].copy_(host, non_blocking=True)
             ready[i % 2].record(copy_stream)
 
     def compute(i):
         torch.cuda.current_stream().wait_event(ready[i % 2])
+        if ingest["raw"]:
+            for j in range(BATCH):      # logical [H, W, D] view of the file-order scan: no copy, out = row j of the batch
+                process_volume(raw_bufs[i % 2][j].permute(2, 1, 0), 1.0, 0.0, 0.75, 1.5, device=dev, out=bufs[i % 2][j])
         x = bufs[i % 2].requires_grad_()
         sim, *_ = clip(None, x, text)
         if world > 1:       # CTCLIP.forward keeps the reference's sim[rank, rank] block layout (ctclip.py:123-127)
@@ -533,7 +552,7 @@ def run_product(args):
         out = torch.cat([sim.detach().flatten(), x.grad.square().sum(dim=(1, 2, 3, 4))])
         x.grad = None
         bufs[i % 2].requires_grad_(False)
-        freed[i % 2].record(torch.cuda.current_stream())
+        freed[i % 2].record(torch.cuda.current_stream())    # (raw mode: also after the preprocess kernels that read raw_bufs)
         res_host[i % 2].copy_(out, non_blocking=True)      # D2H of the step's result into pinned memory
         res_done[i % 2].record(torch.cuda.current_stream())
 
@@ -556,20 +575,29 @@ def run_product(args):
                 res = res_host[(i - 1) % 2].clone()
         res_done[(n - 1) % 2].synchronize()
         return res_host[(n - 1) % 2].clone()
-    run_e2e(max(3, args.warmup))
-    barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 8))
-    res = run_e2e(e2e_steps)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t)
+
+    def time_e2e(raw):
+        ingest["raw"] = raw
+        run_e2e(max(3, args.warmup))
+        barrier()
+        t0 = time.perf_counter()
+        r = run_e2e(e2e_steps)
+        barrier()
+        sec = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([sec], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t)
+        return sec, r
+    e2e_s, res = time_e2e(False)            # fp32 host tensors -> CTCLIP.forward (round 1's definition)
+    raw_s, raw_res = time_e2e(True)         # int16 host scans -> process_volume -> CTCLIP.forward
+    ingest["raw"] = False
     if rank == 0:
         sampler.stop_flag.set()
     e2e_val = BATCH * world / e2e_s
+    raw_val = BATCH * world / raw_s
+    raw_diff = float((raw_res[:BATCH].to(dev) - sim_graph.flatten()).abs().max())
     # the e2e step moves 1.77 GB of fp32 voxels per rank over PCIe: measure this box's pinned H2D rate alone so the
     # bound is visible next to the number (it ranged from 8 to 55 GB/s across the boxes of this pool)
     torch.cuda.synchronize()
@@ -650,7 +678,7 @@ def run_product(args):
         attr_host[:, :, :16] = -1; attr_host[:, :, -16:] = -1
         attr_host[:, :, :, :40] = -1; attr_host[:, :, :, -40:] = -1
         attr_host[..., :40] = -1; attr_host[..., -40:] = -1
-        attr_host = attr_host.pin_memory()
+        attr_host = ((attr_host * 1000).round_().to(torch.int16).float() / 1000).pin_memory()    # as `host` above
     if not args.no_attribution:
         attribution = run_attribution(eng, attr_host, tl, dev, world, dist)
 
@@ -680,22 +708,37 @@ def run_product(args):
         if attribution is not None:
             attribution["cpu_baseline"] = cpu_attribution_baselines()
     step_flops = (FLOP_FWD + FLOP_BWD) * BATCH
+    fp32_block = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4 * world,
+                  "d2h_bytes_per_step": int(res.numel() * 4) * world,
+                  "api": "CTCLIP.forward + sim.backward() on fp32 host tensors; H2D of step i+1 and the host read of step i-1's "
+                         "result overlap the compute of step i (every result is read inside the timed region)",
+                  "bound": "PCIe: max(compute, H2D of the 1.77 GB fp32 batch per rank); compute alone is ms_per_step"}
+    if raw_diff < 1e-3:
+        # headline e2e: the ingest path of the drop-in entry point - the host holds what a .nii.gz scan holds (int16 HU),
+        # the reference's process_file arithmetic runs on the device inside the timed region, half the PCIe bytes
+        e2e_block = {"value": raw_val, "unit": UNIT, "h2d_bytes_per_step": host_raw.numel() * 2 * world,
+                     "d2h_bytes_per_step": int(raw_res.numel() * 4) * world,
+                     "api": "int16 host scans -> process_volume (process_file's HU rescale / resample / clamp / crop-pad, one fused "
+                            "kernel per scan, INSIDE the timed region) -> CTCLIP.forward + sim.backward(); H2D of step i+1 and the "
+                            "host read of step i-1's result overlap the compute of step i",
+                     "input": "int16 HU voxels as stored in the NIfTI file (InferenceDataset / DeviceLoader ship exactly these)",
+                     "logit_max_abs_diff_vs_device_resident_step": raw_diff,
+                     "fp32_host_tensors": fp32_block}
+    else:       # never observed; keep the bench line valid and say so
+        e2e_block = dict(fp32_block, int16_ingest_error=f"logits differ from the device-resident step by {raw_diff:.3e}")
+    e2e_block.update({"h2d_gbps_this_box": h2d_gbps, "steps": e2e_steps, "host_affinity": numa})
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "ctvit_fwd_bwd_b8_480x480x240", "volumes_per_gpu_per_step": BATCH,
+                   "volumes": "int16 HU scans, clamp(350 randn - 200) with an air border; the fp32 volumes are process_file of them",
                    "backward": "input-gradient only (what IG / Grad-CAM run; no weight gradients)",
                    "parallelism": f"volume-sharded dp{world}, no data-path collective",
                    "l2": "inputs (1.77 GB of volumes, >10 GB activations per step) exceed the 126 MB L2",
                    "cuda_graph": f"the {launches_per_step}-launch step is replayed from one CUDA graph in the device-timed region"},
         "model_tflops": step_flops * world / (ms_step / 1e3) / 1e12,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4 * world,
-                "d2h_bytes_per_step": int(res.numel() * 4) * world,
-                "api": "CTCLIP.forward + sim.backward(); H2D of step i+1 and the host read of step i-1's result overlap the "
-                       "compute of step i (every result is read inside the timed region)",
-                "h2d_gbps_this_box": h2d_gbps, "steps": e2e_steps, "host_affinity": numa,
-                "bound": "PCIe: max(compute, H2D of the 1.77 GB fp32 batch per rank); compute alone is ms_per_step"},
+        "e2e": e2e_block,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": sampler.summary(),

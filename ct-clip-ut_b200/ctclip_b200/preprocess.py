@@ -71,10 +71,12 @@ def read_nii_data(file_path) -> Optional[np.ndarray]:
 
 def process_volume(raw, slope: float, intercept: float, xy_spacing: float, z_spacing: float,
                    device: Optional[torch.device] = None, target_spacing=TARGET_SPACING,
-                   target_shape_hwd=TARGET_SHAPE_HWD, pad_value: float = -1.0) -> torch.Tensor:
+                   target_shape_hwd=TARGET_SHAPE_HWD, pad_value: float = -1.0,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`process_file` (preprocess.py:84-151, model_type "ctclip") after the file read: raw voxels of logical shape
-    [H, W, D] (numpy array or tensor; any strides, float32 / float64 / int16) -> fp32 tensor [1, D, H, W] on `device`.
-    One H2D copy of the raw voxels, one kernel."""
+    [H, W, D] (numpy array or tensor, host or device; any strides, float32 / float64 / int16) -> fp32 tensor [1, D, H, W]
+    on `device`.  One H2D copy of the raw voxels (none for a device tensor), one kernel.  `out`: write into this
+    contiguous fp32 [1, D, H, W] device tensor (e.g. one row of a batch buffer) instead of allocating the result."""
     dev = device or torch.device("cuda", torch.cuda.current_device())
     t = torch.from_numpy(raw) if isinstance(raw, np.ndarray) else raw
     if t.dtype not in _KERNEL_DTYPES:
@@ -88,7 +90,10 @@ def process_volume(raw, slope: float, intercept: float, xy_spacing: float, z_spa
     td = td.permute(*inv)                             # logical [H, W, D] view of the device copy
     H0, W0, D0 = td.shape
     Ht, Wt, Dt = target_shape_hwd
-    out = torch.empty(1, Dt, Ht, Wt, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(1, Dt, Ht, Wt, dtype=torch.float32, device=dev)
+    elif (tuple(out.shape) != (1, Dt, Ht, Wt) or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous()):
+        raise ValueError(f"out must be a contiguous fp32 CUDA tensor of shape {(1, Dt, Ht, Wt)}, got {tuple(out.shape)} {out.dtype}")
     res = (ctypes.c_int * 3)()
     call("ctc_preprocess_ct", td, _KERNEL_DTYPES[td.dtype], H0, W0, D0, td.stride(0), td.stride(1), td.stride(2),
          float(np.float32(slope)), float(np.float32(intercept)), float(z_spacing), float(xy_spacing),
