@@ -63,3 +63,17 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.split()[0] == "100", (r.stdout, r.stderr)
+
+
+def test_gemm_row_perm_is_the_documented_permutation():
+    """ctc_gemm_row_perm (host-side, no GPU): accumulator column 8 j + 2 q + e of a 32-column group holds channel
+    8 q + 2 j + e (include/ctclip_b200.h) - the packing Plan._pack applies to every GEMM weight."""
+    import ctypes
+    from ctclip_b200 import _lib
+    perm = _lib.gemm_row_perm()
+    assert sorted(perm) == list(range(32))
+    for j in range(4):
+        for q in range(4):
+            for e in range(2):
+                assert perm[8 * j + 2 * q + e] == 8 * q + 2 * j + e
+    assert _lib.GEMM_BPERM == 0x100
