@@ -1,13 +1,17 @@
 // Dense bf16 GEMM family for the CTViT linears:  C[M,N] = A[M,K] · B[N,K]ᵀ  (fp32 accumulate).
 //
 // sm_100a design: persistent, warp-specialised kernel, one CTA per SM.
-//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, mbarrier ring: 4 stages, 6 in pair mode)
-//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma kind::f16, M=128, N=BN, K=16)
+//   warp 0      TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, mbarrier ring: 4 stages, 6 / 7 in pair mode)
+//   warp 1      MMA issuer     (tcgen05.mma kind::f16, M=128, N=BN, K=16; four per 64-deep k-block)
+//               both run CONVERGED with one elect.sync lane issuing, so that descriptors / coordinates live in uniform
+//               registers (inside an `if (lane == 0)` region every instruction is wrapped in a scalarisation loop)
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global); a warp may
-//               only touch TMEM lanes 32*(warp%4)..+31, so warps w and w+4 share a lane quarter and
-//               split the tile's columns in halves: the epilogues that do real arithmetic per element
-//               (GEGLU, VQ top-2) and the residual loads get 8 warps of issue slots / loads in flight
+//   warps 4-..  epilogue, EW = 8 or 16 warps; a warp may only touch TMEM lanes 32*(warp%4)..+31, so the warps that
+//               share a lane quarter split the tile's columns.  Two families:
+//               staged  (B as nn.Linear stores it): tcgen05.ld 32x32b -> registers -> fused epilogue -> per-warp
+//                        swizzled shared-memory tile -> coalesced 16-byte global accesses
+//               direct  (B rows permuted inside 32-row groups at plan time, CTC_GEMM_BPERM): tcgen05.ld 16x256b ->
+//                        registers -> fused epilogue -> global, no shared memory (the product path; bit-identical)
 // The accumulator lives in TMEM and is double buffered, so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Both operands are K-major ("row-major [rows, K]"), which is exactly the
 // nn.Linear weight layout [out_features, in_features] (reference: src/utils/attention.py:47,49,
