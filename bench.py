@@ -322,6 +322,25 @@ def occlusion_flops(T=24, HW=576, n_layers=4, nt=2):
     return dense + FLOP_FWD, execd + FLOP_FWD, n
 
 
+def synthetic_scans(seed, batch, shape=(240, 480, 480), border=(16, 40, 40)):
+    """Synthetic CT scans: clamp(0.35 randn - 0.2) with an air border, stored the way a NIfTI file stores
+    them - int16 Hounsfield units (slope 1, intercept 0, already at the target spacing and shape, so that `process_file`'s
+    arithmetic reduces to clamp(hu) / 1000).  Returns (fp32 volumes [batch, 1, D, H, W] = process_file of the scans,
+    int16 scans in FILE ORDER: memory [batch, D, W, H], i.e. the first NIfTI axis i = H fastest, then j = W, then k = D).
+    The first scan of a batch depends on the seed only, not on `batch` (a prefix of the same generator stream), which is
+    what lets every rank rebuild rank 0's first volume for the latency mode without a collective."""
+    import torch
+    D, H, W = shape
+    g = torch.Generator().manual_seed(seed)
+    v = (0.35 * torch.randn(batch, 1, D, H, W, generator=g) - 0.2).clamp_(-1, 1)
+    bd, bh, bw = border
+    v[:, :, :bd] = -1; v[:, :, -bd:] = -1
+    v[:, :, :, :bh] = -1; v[:, :, :, -bh:] = -1
+    v[..., :bw] = -1; v[..., -bw:] = -1
+    hu = (v * 1000).round_().to(torch.int16).squeeze(1)                      # [batch, D, H, W]
+    return (hu.float() / 1000).unsqueeze(1).contiguous(), hu.permute(0, 1, 3, 2).contiguous()
+
+
 def run_attribution(eng, host_vol, tl, dev, world, dist):
     """BASELINE.json's first metric: attributed CT volumes/s = one 480x480x240 volume through the full occlusion
     sweep ((20,40,40)/(10,20,20): 12 167 windows, visualizations.py:335-424) plus 50-step integrated gradients
@@ -449,19 +468,8 @@ def run_product(args):
     eng = clip.engine(dev)
 
     # ---- synthetic data: clamp(0.35 randn - 0.2) with a -1 border; pinned host buffers for e2e
-    g = torch.Generator().manual_seed(1234 + rank)
-    host = (0.35 * torch.randn(BATCH, 1, 240, 480, 480, generator=g) - 0.2).clamp_(-1, 1)
-    host[:, :, :16] = -1; host[:, :, -16:] = -1
-    host[:, :, :, :40] = -1; host[:, :, :, -40:] = -1
-    host[..., :40] = -1; host[..., -40:] = -1
-    # the scans as a NIfTI file stores them: int16 Hounsfield units (slope 1, intercept 0, already at the target spacing
-    # and shape, so that `process_file`'s arithmetic reduces to clamp(hu) / 1000); every arm of the bench runs on exactly
-    # these volumes - the fp32 tensors ARE preprocess(hu)
-    hu = (host * 1000).round_().to(torch.int16).squeeze(1)                                       # [B, D, H, W]
-    host = (hu.float() / 1000).unsqueeze(1).contiguous().pin_memory()
-    # NIfTI file order: the first axis (i = H) fastest, then j = W, then k = D - the bytes a reader hands over unchanged
-    host_raw = hu.permute(0, 1, 3, 2).contiguous().pin_memory()                                  # memory [B, D, W, H]
-    del hu
+    host, host_raw = synthetic_scans(1234 + rank, BATCH)
+    host, host_raw = host.pin_memory(), host_raw.pin_memory()
     text = torch.randn(1, 768, generator=torch.Generator().manual_seed(7)).to(dev)
     vol = host.to(dev)
     tl = eng.text_latents(text)
@@ -673,12 +681,7 @@ def run_product(args):
     # other ranks (the first 55.3 M numbers of the same generator) - no collective before the timed region.
     attr_host = host[:1]
     if world > 1 and rank != 0 and not (args.no_attribution and args.no_parity):
-        g0 = torch.Generator().manual_seed(1234)
-        attr_host = (0.35 * torch.randn(1, 1, 240, 480, 480, generator=g0) - 0.2).clamp_(-1, 1)
-        attr_host[:, :, :16] = -1; attr_host[:, :, -16:] = -1
-        attr_host[:, :, :, :40] = -1; attr_host[:, :, :, -40:] = -1
-        attr_host[..., :40] = -1; attr_host[..., -40:] = -1
-        attr_host = ((attr_host * 1000).round_().to(torch.int16).float() / 1000).pin_memory()    # as `host` above
+        attr_host = synthetic_scans(1234, 1)[0].pin_memory()      # == rank 0's host[:1] (tests/test_bench_contract.py)
     if not args.no_attribution:
         attribution = run_attribution(eng, attr_host, tl, dev, world, dist)
 

@@ -40,3 +40,24 @@ def test_attribution_flop_bookkeeping():
     total = dense + 50 * (b.FLOP_FWD + b.FLOP_BWD)
     assert abs(total / 1e15 - 9.683) < 5e-3
     assert 0.60 < executed / dense < 0.65
+
+
+def test_synthetic_scans_prefix_and_file_order():
+    """bench.synthetic_scans: (1) the first scan of a batch depends on the seed only - every rank rebuilds rank 0's first
+    volume for the sharded latency mode / the N-rank parity check from it (a per-rank volume made that check fail in round
+    2); (2) the fp32 volume is clamp(hu) / 1000 of the int16 scan, which is stored in NIfTI file order (H fastest)."""
+    import importlib.util
+    from pathlib import Path
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    shape, border = (16, 48, 32), (2, 4, 4)
+    v8, r8 = bench.synthetic_scans(1234, 8, shape, border)
+    v1, r1 = bench.synthetic_scans(1234, 1, shape, border)
+    assert torch.equal(v8[:1], v1) and torch.equal(r8[:1], r1)
+    assert not torch.equal(bench.synthetic_scans(1235, 1, shape, border)[0], v1)
+    assert v8.shape == (8, 1, 16, 48, 32) and r8.shape == (8, 16, 32, 48) and r8.dtype == torch.int16
+    hu = r8.permute(0, 1, 3, 2)                                   # logical [B, D, H, W]
+    assert torch.equal(v8[:, 0], hu.float() / 1000)
+    assert float(v8.min()) == -1.0 and float(v8.max()) <= 1.0 and torch.all(v8[:, :, :2] == -1)
